@@ -1,0 +1,61 @@
+"""Build libBridge.so (the C-ABI CUDA library) in-tree for sm_100a with nvcc.
+
+    python rvdd-release_b200/build.py          # builds rvdd-release_b200/lib/libBridge.so and ./build/libBridge.so
+
+The second copy sits where the reference code looks for it ('./build/libBridge.so' relative to the working
+directory: util/flow_utils.py:129,145, data/axel4rec_dataset.py:65 in the reference).  Both are git-ignored and
+travel to the GPU box with the gpurun snapshot.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+SOURCES = ["bridge.cu", "prep.cu", "solver.cu", "warp.cu"]
+LIB = os.path.join(PKG, "lib", "libBridge.so")
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "rvdd_bridge.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_lib(force=False, verbose=False):
+    """Compile csrc/*.cu -> lib/libBridge.so (sm_100a).  Returns the library path."""
+    if not force and not needs_build():
+        return LIB
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    objdir = os.path.join(PKG, "lib", "obj")
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = _nvcc()
+    objs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        subprocess.run(cmd, check=True)
+        objs.append(obj)
+    tmp = LIB + ".tmp"
+    subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs, check=True)
+    os.replace(tmp, LIB)
+    os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
+    shutil.copy2(LIB, os.path.join(ROOT, "build", "libBridge.so"))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))

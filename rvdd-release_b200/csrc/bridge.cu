@@ -1,0 +1,508 @@
+// bridge.cu -- the C ABI of libBridge.so (include/rvdd_bridge.h): context / workspace arena, the host-side
+// pyramid driver that queues the kernels of prep.cu, solver.cu and warp.cu on a stream, the drop-in
+// `tvl1flow` symbol (libBridge.cpp:44) and the host-buffer end-to-end entry point.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <cmath>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/rvdd_bridge.h"
+#include "internal.h"
+
+using namespace rvdd;
+
+// ------------------------------------------------------------------------------------------------ errors
+
+static thread_local std::string g_err;
+
+static int fail(const char *what, cudaError_t e = cudaSuccess)
+{
+    g_err = what;
+    if (e != cudaSuccess) {
+        g_err += ": ";
+        g_err += cudaGetErrorString(e);
+    }
+    return e != cudaSuccess ? (int)e : -1;
+}
+
+#define CK(call)                                         \
+    do {                                                 \
+        cudaError_t e_ = (call);                         \
+        if (e_ != cudaSuccess) return fail(#call, e_);   \
+    } while (0)
+
+extern "C" const char *rvdd_last_error(void) { return g_err.c_str(); }
+extern "C" int rvdd_abi_version(void) { return RVDD_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------------------------ parameters
+
+extern "C" void rvdd_default_params(rvdd_tvl1_params *p)
+{
+    // libBridge.cpp:27-36
+    p->tau = 0.25;
+    p->lambda = 0.15;
+    p->theta = 0.3;
+    p->nscales = 100;
+    p->fscale = 0;
+    p->zfactor = 0.5;
+    p->nwarps = 5;
+    p->epsilon = 0.01;
+}
+
+// parameter checks of libBridge.cpp:60-123 (out-of-range values fall back to the defaults)
+static rvdd_tvl1_params sanitize(const rvdd_tvl1_params *in)
+{
+    rvdd_tvl1_params d, p;
+    rvdd_default_params(&d);
+    p = in ? *in : d;
+    if (p.tau <= 0 || p.tau > 0.25) p.tau = d.tau;
+    if (p.lambda <= 0) p.lambda = d.lambda;
+    if (p.theta <= 0) p.theta = d.theta;
+    if (p.nscales <= 0) p.nscales = d.nscales;
+    if (p.zfactor <= 0 || p.zfactor >= 1) p.zfactor = d.zfactor;
+    if (p.nwarps <= 0) p.nwarps = d.nwarps;
+    if (p.epsilon <= 0) p.epsilon = d.epsilon;
+    return p;
+}
+
+// libBridge.cpp:131-138 (same C++ expression, so the same float/double overloads are picked) + zoom.c:22-34
+static void build_pyramid(int nx, int ny, rvdd_tvl1_params &p, Pyramid &P)
+{
+    float zfactor = p.zfactor;
+    int nscales = p.nscales;
+    const float N = 1 + log(hypot(nx, ny) / 16.0) / log(1 / zfactor);
+    if (N < nscales) nscales = N;
+    if (nscales < p.fscale) p.fscale = nscales;
+    if (nscales > RVDD_MAX_SCALES) nscales = RVDD_MAX_SCALES;
+    if (nscales < 1) nscales = 1;
+    p.nscales = nscales;
+    P.S = nscales;
+    P.nx[0] = nx;
+    P.ny[0] = ny;
+    long long off = 0;
+    for (int s = 0; s < nscales; s++) {
+        if (s > 0) {
+            P.nx[s] = (int)((float)P.nx[s - 1] * zfactor + 0.5);
+            P.ny[s] = (int)((float)P.ny[s - 1] * zfactor + 0.5);
+        }
+        P.off[s] = off;
+        off += ((long long)P.nx[s] * P.ny[s] + 3) & ~3LL;
+    }
+    P.total = off;
+}
+
+extern "C" int rvdd_pyramid(int nx, int ny, const rvdd_tvl1_params *params, int *nxs, int *nys)
+{
+    rvdd_tvl1_params p = sanitize(params);
+    Pyramid P;
+    build_pyramid(nx, ny, p, P);
+    for (int s = 0; s < P.S; s++) {
+        if (nxs) nxs[s] = P.nx[s];
+        if (nys) nys[s] = P.ny[s];
+    }
+    return P.S;
+}
+
+// mask.c:224-246
+static int make_taps(double sigma, GaussTaps &t)
+{
+    const double den = 2 * sigma * sigma;
+    const int size = (int)(5 * sigma) + 1;
+    if (size > RVDD_MAX_TAPS) return -1;
+    t.size = size;
+    for (int i = 0; i < size; i++) t.B[i] = 1 / (sigma * sqrt(2.0 * 3.1415926)) * exp(-i * i / den);
+    double norm = 0;
+    for (int i = 0; i < size; i++) norm += t.B[i];
+    norm *= 2;
+    norm -= t.B[0];
+    for (int i = 0; i < size; i++) t.B[i] /= norm;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ context
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+#define RING 4
+
+struct rvdd_ctx {
+    int device = 0, sms = 0, ctas_per_sm = 0;
+    int req_groups = 0;
+    DevBuf pyr, tmp, scratch, small, table;
+    // pinned staging ring for the pointer tables
+    void *ring_host[RING] = {nullptr, nullptr, nullptr, nullptr};
+    size_t ring_cap[RING] = {0, 0, 0, 0};
+    cudaEvent_t ring_ev[RING] = {nullptr, nullptr, nullptr, nullptr};
+    int ring_next = 0;
+    int *status_dev = nullptr;
+    Pyramid last_pyr;                   // geometry of the last rvdd_tvl1_flow_dev call (for rvdd_debug_level_dev)
+    int last_pairs = 0;
+    // end-to-end staging (rvdd_flow_and_warp_host, tvl1flow)
+    DevBuf e_frames, e_gray, e_flow, e_hw2, e_warp, e_iters;
+    cudaStream_t st_compute = nullptr, st_in = nullptr, st_out = nullptr;
+    std::vector<cudaEvent_t> events;
+};
+
+extern "C" int rvdd_create(rvdd_ctx **out)
+{
+    if (!out) return fail("rvdd_create: null out");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail("rvdd_create: no CUDA device (there is no CPU fallback)", e);
+    rvdd_ctx *c = new rvdd_ctx();
+    CK(cudaGetDevice(&c->device));
+    int coop = 0;
+    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
+    if (!coop) {
+        delete c;
+        return fail("rvdd_create: device lacks cooperative launch");
+    }
+    e = solver_max_ctas(&c->ctas_per_sm, &c->sms);
+    if (e != cudaSuccess || c->ctas_per_sm < 1) {
+        delete c;
+        return fail("rvdd_create: solver kernel does not fit on this device", e);
+    }
+    for (int i = 0; i < RING; i++) CK(cudaEventCreateWithFlags(&c->ring_ev[i], cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&c->st_compute, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking));
+    *out = c;
+    return 0;
+}
+
+extern "C" int rvdd_destroy(rvdd_ctx *c)
+{
+    if (!c) return 0;
+    cudaDeviceSynchronize();
+    c->pyr.release(); c->tmp.release(); c->scratch.release(); c->small.release(); c->table.release();
+    c->e_frames.release(); c->e_gray.release(); c->e_flow.release(); c->e_hw2.release(); c->e_warp.release();
+    c->e_iters.release();
+    for (int i = 0; i < RING; i++) {
+        if (c->ring_host[i]) cudaFreeHost(c->ring_host[i]);
+        if (c->ring_ev[i]) cudaEventDestroy(c->ring_ev[i]);
+    }
+    for (cudaEvent_t ev : c->events) cudaEventDestroy(ev);
+    if (c->st_compute) cudaStreamDestroy(c->st_compute);
+    if (c->st_in) cudaStreamDestroy(c->st_in);
+    if (c->st_out) cudaStreamDestroy(c->st_out);
+    delete c;
+    return 0;
+}
+
+extern "C" int rvdd_set_groups(rvdd_ctx *c, int n)
+{
+    if (!c) return fail("rvdd_set_groups: null context");
+    c->req_groups = n < 0 ? 0 : n;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ TV-L1 driver
+
+extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, int nx, int ny, const int *src,
+                                  const int *tgt, int npairs, const rvdd_tvl1_params *params, float *flow,
+                                  int *iters, void *stream)
+{
+    if (!c) return fail("rvdd_tvl1_flow_dev: null context");
+    if (npairs <= 0) return 0;
+    if (!gray || !src || !tgt || !flow) return fail("rvdd_tvl1_flow_dev: null argument");
+    if (nx < 4 || ny < 4 || (long long)nx * ny > (1LL << 30)) return fail("rvdd_tvl1_flow_dev: unsupported image size");
+    cudaStream_t st = (cudaStream_t)stream;
+    rvdd_tvl1_params p = sanitize(params);
+    Pyramid P;
+    build_pyramid(nx, ny, p, P);
+    const int S = P.S, K = npairs;
+    for (int k = 0; k < K; k++)
+        if (src[k] < 0 || src[k] >= nframes || tgt[k] < 0 || tgt[k] >= nframes)
+            return fail("rvdd_tvl1_flow_dev: pair index out of range");
+
+    GaussTaps pre, zoom;
+    if (make_taps(RVDD_PRESMOOTH_SIGMA, pre)) return fail("presmoothing kernel too wide");
+    const float zsigma = RVDD_ZOOM_SIGMA_ZERO * sqrt(1.0 / (double)(p.zfactor * p.zfactor) - 1.0);   // zoom.c:59
+    if (S > 1 && make_taps((double)zsigma, zoom)) return fail("zoom kernel too wide (zfactor too small)");
+    if (pre.size > nx || pre.size > ny) return fail("image smaller than the presmoothing kernel (mask.c:229)");
+    for (int s = 0; s + 1 < S; s++)
+        if (zoom.size > P.nx[s] || zoom.size > P.ny[s]) return fail("pyramid level smaller than the zoom kernel (mask.c:229)");
+
+    // ---- groups and workspace
+    const int total_ctas = c->sms * c->ctas_per_sm;
+    int G = c->req_groups > 0 ? c->req_groups : (K < 8 ? K : 8);
+    if (G > K) G = K;
+    if (G > total_ctas) G = total_ctas;
+    const int C = total_ctas / G;
+    const long long plane = ((long long)nx * ny + 3) & ~3LL;
+    const long long scratch_stride = 18 * plane;
+    CK(c->pyr.ensure(sizeof(float) * (size_t)(2 * K) * P.total));
+    CK(c->tmp.ensure(sizeof(float) * (size_t)(2 * K) * plane));
+    CK(c->scratch.ensure(sizeof(float) * (size_t)G * scratch_stride));
+    // small: [slots 2K ints][status 32 ints][bar G*32 uints][partials G*2*C doubles]
+    const size_t off_status = ((size_t)2 * K * sizeof(int) + 255) & ~(size_t)255;
+    const size_t off_bar = off_status + 256;
+    const size_t off_part = (off_bar + (size_t)G * 32 * sizeof(unsigned) + 255) & ~(size_t)255;
+    CK(c->small.ensure(off_part + sizeof(double) * (size_t)G * 2 * C));
+    CK(c->table.ensure(sizeof(void *) * (size_t)2 * K));
+    char *small = (char *)c->small.p;
+    int *slots = (int *)small;
+    int *status = (int *)(small + off_status);
+    unsigned *bar = (unsigned *)(small + off_bar);
+    double *partials = (double *)(small + off_part);
+    c->status_dev = status;
+    c->last_pyr = P;
+    c->last_pairs = K;
+
+    // ---- pointer table (I0 of every pair, then I1 of every pair) through a pinned ring slot
+    const int slot = c->ring_next;
+    c->ring_next = (c->ring_next + 1) % RING;
+    const size_t tbytes = sizeof(void *) * (size_t)2 * K;
+    CK(cudaEventSynchronize(c->ring_ev[slot]));
+    if (c->ring_cap[slot] < tbytes) {
+        if (c->ring_host[slot]) cudaFreeHost(c->ring_host[slot]);
+        c->ring_host[slot] = nullptr;
+        c->ring_cap[slot] = 0;
+        CK(cudaMallocHost(&c->ring_host[slot], tbytes));
+        c->ring_cap[slot] = tbytes;
+    }
+    const float **tab = (const float **)c->ring_host[slot];
+    for (int k = 0; k < K; k++) {
+        tab[k] = gray + (long long)tgt[k] * nx * ny;          // I0 = target frame (flow_utils.py:149)
+        tab[K + k] = gray + (long long)src[k] * nx * ny;      // I1 = source frame
+    }
+    const float *const *dtab = (const float *const *)c->table.p;
+    CK(cudaMemcpyAsync(c->table.p, tab, tbytes, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(c->ring_ev[slot], st));
+
+    // ---- pyramid: normalise + presmooth (tvl1flow_lib.c:380-384), then zoom_out per level (:387-401)
+    float *pyr = (float *)c->pyr.p, *tmp = (float *)c->tmp.p;
+    CK(launch_setup(slots, K, bar, G * 32, status, st));
+    CK(launch_minmax(dtab, dtab + K, nx * ny, K, slots, st));
+    CK(launch_gauss(dtab, nullptr, 0, pyr, P.total, nx, ny, 2 * K, pre, slots, K, st));
+    for (int s = 1; s < S; s++) {
+        CK(launch_gauss(nullptr, pyr + P.off[s - 1], P.total, tmp, plane, P.nx[s - 1], P.ny[s - 1], 2 * K, zoom, nullptr, K, st));
+        CK(launch_resample(tmp, plane, P.nx[s - 1], P.ny[s - 1], pyr + P.off[s], P.total, P.nx[s], P.ny[s], p.zfactor,
+                           p.zfactor, 2 * K, st));
+    }
+
+    // ---- persistent solver
+    SolverArgs A;
+    memset(&A, 0, sizeof A);
+    A.npairs = K; A.S = S; A.fscale = p.fscale; A.nwarps = p.nwarps;
+    for (int s = 0; s < S; s++) {
+        A.nx[s] = P.nx[s]; A.ny[s] = P.ny[s]; A.off[s] = P.off[s];
+        if (s + 1 < S) {
+            A.zfx[s] = ((float)P.nx[s] / P.nx[s + 1]);      // zoom.c:95-96
+            A.zfy[s] = ((float)P.ny[s] / P.ny[s + 1]);
+        }
+    }
+    A.l_t = p.lambda * p.theta;                              // tvl1flow_lib.c:107
+    A.theta = p.theta;
+    A.taut = p.tau / p.theta;                                // :233
+    A.eps2 = p.epsilon * p.epsilon;                          // :163
+    A.zoom_mul = (float)1.0 / p.zfactor;                     // :431
+    A.pyr0 = pyr; A.pyr1 = pyr + (long long)K * P.total; A.pyr_stride = P.total;
+    A.flow_out = flow;
+    A.scratch = (float *)c->scratch.p; A.scratch_stride = scratch_stride; A.plane = plane;
+    A.iters_out = iters; A.err_out = nullptr;
+    A.bar = bar; A.partials = partials; A.status = status;
+    A.ngroups = G; A.ctas_per_group = C;
+    A.spin_limit = 4000000000LL;                             // ~2 s at 2 GHz
+    if (iters) CK(cudaMemsetAsync(iters, 0, sizeof(int) * (size_t)K * RVDD_TRACE_SCALES * p.nwarps, st));
+    CK(launch_solver(A, st));
+    return 0;
+}
+
+extern "C" int rvdd_solver_status(rvdd_ctx *c, void *stream)
+{
+    if (!c) return fail("rvdd_solver_status: null context");
+    if (!c->status_dev) return 0;
+    int v = 0;
+    CK(cudaMemcpyAsync(&v, c->status_dev, sizeof v, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    if (v) fail("solver watchdog fired: a group barrier timed out, results are invalid");
+    return v;
+}
+
+extern "C" int rvdd_debug_level_dev(rvdd_ctx *c, int pair, int which, int level, float *dst, void *stream)
+{
+    if (!c || !c->pyr.p) return fail("rvdd_debug_level_dev: no pyramid in the workspace");
+    const Pyramid &P = c->last_pyr;
+    if (pair < 0 || pair >= c->last_pairs || level < 0 || level >= P.S || (which != 0 && which != 1))
+        return fail("rvdd_debug_level_dev: index out of range");
+    const float *src = (const float *)c->pyr.p + ((long long)which * c->last_pairs + pair) * P.total + P.off[level];
+    CK(cudaMemcpyAsync(dst, src, sizeof(float) * (size_t)P.nx[level] * P.ny[level], cudaMemcpyDeviceToDevice,
+                       (cudaStream_t)stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ thin wrappers
+
+extern "C" int rvdd_gray_dev(const float *img, float *gray, int nimg, int h, int w, int ch, void *stream)
+{
+    if (!img || !gray) return fail("rvdd_gray_dev: null argument");
+    if (ch != 1 && ch != 3 && ch != 4) return fail("rvdd_gray_dev: channels must be 1, 3 or 4 (library.py:162-170)");
+    CK(launch_gray(img, gray, (long long)nimg * h * w, ch, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int rvdd_warp_dev(const float *x, const float *flow, float *out, float *mask, int B, int C, int H, int W,
+                             long long xs_b, long long xs_c, long long xs_h, long long xs_w, long long os_b,
+                             long long os_c, long long os_h, long long os_w, int fh, int fw, float flow_mul, int interp,
+                             void *stream)
+{
+    if (!x || !flow || !out) return fail("rvdd_warp_dev: null argument");
+    if (interp != 0 && interp != 1) return fail("rvdd_warp_dev: interp must be 0 (bilinear) or 1 (bicubic)");
+    if (!((fh == H && fw == W) || (2 * fh == H && 2 * fw == W))) return fail("rvdd_warp_dev: flow grid must be (H,W) or (H/2,W/2)");
+    if (B > 65535) return fail("rvdd_warp_dev: batch too large");
+    WarpArgs a;
+    a.x = x; a.flow = flow; a.out = out; a.mask = mask;
+    a.B = B; a.C = C; a.H = H; a.W = W;
+    a.xs_b = xs_b; a.xs_c = xs_c; a.xs_h = xs_h; a.xs_w = xs_w;
+    a.os_b = os_b; a.os_c = os_c; a.os_h = os_h; a.os_w = os_w;
+    a.fh = fh; a.fw = fw; a.flow_mul = flow_mul; a.interp = interp;
+    CK(launch_warp(a, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int rvdd_upsample2_dev(const float *in, float *out, long long planes, int h, int w, float mul, void *stream)
+{
+    if (!in || !out) return fail("rvdd_upsample2_dev: null argument");
+    CK(launch_upsample2(in, out, planes, h, w, mul, (cudaStream_t)stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ host entry points
+
+// planar [2][n] -> chunky [n][2] (library.py:175 returns the (h, w, 2) view; base_dataset.py:180 writes it)
+__global__ void interleave_kernel(const float *__restrict__ planar, float2 *__restrict__ hw2, long long n)
+{
+    const long long k = blockIdx.y;
+    const float *p = planar + k * 2 * n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        hw2[k * n + i] = make_float2(p[i], p[n + i]);
+}
+
+extern "C" int rvdd_flow_and_warp_host(rvdd_ctx *c, const float *frames, int nframes, int h, int w, int ch,
+                                       const int *src, const int *tgt, int npairs, const rvdd_tvl1_params *params,
+                                       float *flow_host, float *warped_host, int *iters_host)
+{
+    if (!c) return fail("rvdd_flow_and_warp_host: null context");
+    if (npairs <= 0) return 0;
+    if (!frames || !src || !tgt || !flow_host) return fail("rvdd_flow_and_warp_host: null argument");
+    if (ch != 1 && ch != 3 && ch != 4) return fail("rvdd_flow_and_warp_host: channels must be 1, 3 or 4");
+    const long long n = (long long)h * w;
+    const rvdd_tvl1_params p = sanitize(params);
+    cudaStream_t st = c->st_compute;
+    CK(c->e_frames.ensure(sizeof(float) * (size_t)nframes * n * ch));
+    CK(c->e_gray.ensure(sizeof(float) * (size_t)nframes * n));
+    CK(c->e_flow.ensure(sizeof(float) * (size_t)npairs * 2 * n));
+    CK(c->e_hw2.ensure(sizeof(float) * (size_t)npairs * 2 * n));
+    if (warped_host) CK(c->e_warp.ensure(sizeof(float) * (size_t)npairs * n * ch));
+    if (iters_host) CK(c->e_iters.ensure(sizeof(int) * (size_t)npairs * RVDD_TRACE_SCALES * p.nwarps));
+    float *d_frames = (float *)c->e_frames.p, *d_gray = (float *)c->e_gray.p, *d_flow = (float *)c->e_flow.p;
+    float *d_hw2 = (float *)c->e_hw2.p, *d_warp = (float *)c->e_warp.p;
+    int *d_iters = iters_host ? (int *)c->e_iters.p : nullptr;
+
+    // events: one per frame (upload done) + one (compute done)
+    while ((int)c->events.size() < nframes + 1) {
+        cudaEvent_t ev;
+        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        c->events.push_back(ev);
+    }
+    // upload frame by frame on the copy-in stream; gray conversion follows each frame on the compute stream
+    for (int f = 0; f < nframes; f++) {
+        CK(cudaMemcpyAsync(d_frames + (long long)f * n * ch, frames + (long long)f * n * ch, sizeof(float) * n * ch,
+                           cudaMemcpyHostToDevice, c->st_in));
+        CK(cudaEventRecord(c->events[f], c->st_in));
+        CK(cudaStreamWaitEvent(st, c->events[f], 0));
+        CK(launch_gray(d_frames + (long long)f * n * ch, d_gray + (long long)f * n, n, ch, st));
+    }
+    int rc = rvdd_tvl1_flow_dev(c, d_gray, nframes, w, h, src, tgt, npairs, &p, d_flow, d_iters, st);
+    if (rc) return rc;
+    {
+        unsigned bx = (unsigned)((n + 255) / 256);
+        if (bx > 592) bx = 592;
+        interleave_kernel<<<dim3(bx, npairs), 256, 0, st>>>(d_flow, (float2 *)d_hw2, n);
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(flow_host, d_hw2, sizeof(float) * (size_t)npairs * 2 * n, cudaMemcpyDeviceToHost, st));
+    if (warped_host) {
+        // single_warp(img1 = source frame, flow) in the frames' own HWC layout (flow_utils.py:105-122, :154)
+        for (int k = 0; k < npairs; k++) {
+            WarpArgs a;
+            a.x = d_frames + (long long)src[k] * n * ch;
+            a.flow = d_flow + (long long)k * 2 * n;
+            a.out = d_warp + (long long)k * n * ch;
+            a.mask = nullptr;
+            a.B = 1; a.C = ch; a.H = h; a.W = w;
+            a.xs_b = a.os_b = n * ch; a.xs_c = a.os_c = 1; a.xs_h = a.os_h = (long long)w * ch; a.xs_w = a.os_w = ch;
+            a.fh = h; a.fw = w; a.flow_mul = 1.0f; a.interp = 1;
+            CK(launch_warp(a, st));
+        }
+        CK(cudaMemcpyAsync(warped_host, d_warp, sizeof(float) * (size_t)npairs * n * ch, cudaMemcpyDeviceToHost, st));
+    }
+    if (iters_host)
+        CK(cudaMemcpyAsync(iters_host, d_iters, sizeof(int) * (size_t)npairs * RVDD_TRACE_SCALES * p.nwarps,
+                           cudaMemcpyDeviceToHost, st));
+    int rs = rvdd_solver_status(c, st);   // synchronises the compute stream
+    if (rs) return rs;
+    return 0;
+}
+
+// The reference symbol (libBridge.cpp:44): host float buffers, default parameters, planar (u, v) result.
+static std::mutex g_mu;
+static rvdd_ctx *g_ctx = nullptr;
+
+extern "C" void tvl1flow(float *I0, float *I1, float *u, int nx, int ny)
+{
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!g_ctx && rvdd_create(&g_ctx)) {
+        fprintf(stderr, "libBridge(tvl1flow): %s\n", rvdd_last_error());
+        g_ctx = nullptr;
+        return;
+    }
+    rvdd_ctx *c = g_ctx;
+    const size_t n = (size_t)nx * ny;
+    cudaStream_t st = c->st_compute;
+    auto bail = [&](const char *what, cudaError_t e) {
+        fail(what, e);
+        fprintf(stderr, "libBridge(tvl1flow): %s\n", rvdd_last_error());
+    };
+    cudaError_t e;
+    if ((e = c->e_gray.ensure(sizeof(float) * 2 * n)) != cudaSuccess) return bail("alloc", e);
+    if ((e = c->e_flow.ensure(sizeof(float) * 2 * n)) != cudaSuccess) return bail("alloc", e);
+    float *d_gray = (float *)c->e_gray.p, *d_flow = (float *)c->e_flow.p;
+    if ((e = cudaMemcpyAsync(d_gray, I0, sizeof(float) * n, cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail("H2D", e);
+    if ((e = cudaMemcpyAsync(d_gray + n, I1, sizeof(float) * n, cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail("H2D", e);
+    const int src = 1, tgt = 0;
+    if (rvdd_tvl1_flow_dev(c, d_gray, 2, nx, ny, &src, &tgt, 1, nullptr, d_flow, nullptr, st)) {
+        fprintf(stderr, "libBridge(tvl1flow): %s\n", rvdd_last_error());
+        return;
+    }
+    if (rvdd_solver_status(c, st)) {
+        fprintf(stderr, "libBridge(tvl1flow): %s\n", rvdd_last_error());
+        return;
+    }
+    if ((e = cudaMemcpyAsync(u, d_flow, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return bail("D2H", e);
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return bail("sync", e);
+}

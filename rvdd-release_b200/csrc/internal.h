@@ -1,0 +1,77 @@
+// internal.h -- host-side declarations shared by the .cu files of libBridge.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "exact_math.h"
+
+namespace rvdd {
+
+// Geometry of one pyramid, computed on the host exactly as zoom_size / libBridge.cpp do.
+struct Pyramid {
+    int S;                              // number of scales actually used
+    int nx[RVDD_MAX_SCALES], ny[RVDD_MAX_SCALES];
+    long long off[RVDD_MAX_SCALES];     // element offset of level s inside a per-image pyramid buffer
+    long long total;                    // elements per image pyramid (padded so every level is 16 B aligned)
+};
+
+struct GaussTaps {
+    int size;                           // taps B[0..size-1] (mask.c:225)
+    double B[RVDD_MAX_TAPS];
+};
+
+// Arguments of the persistent solver kernel (solver.cu).
+struct SolverArgs {
+    int npairs, S, fscale, nwarps;
+    int nx[RVDD_MAX_SCALES], ny[RVDD_MAX_SCALES];
+    long long off[RVDD_MAX_SCALES];
+    float zfx[RVDD_MAX_SCALES], zfy[RVDD_MAX_SCALES];   // zoom_in factors towards level s (from s+1), zoom.c:95-96
+    float l_t, theta, taut, eps2, zoom_mul;
+    const float *pyr0, *pyr1;           // [npairs][pyr_stride]
+    long long pyr_stride;
+    float *flow_out;                    // [npairs][2][nx0*ny0]
+    float *scratch;                     // [ngroups][scratch_stride]
+    long long scratch_stride, plane;    // plane = padded nx0*ny0
+    int *iters_out;                     // [npairs][RVDD_MAX_SCALES][nwarps] or null
+    float *err_out;                     // same shape, error at loop exit, or null
+    unsigned *bar;                      // [ngroups * 32] (one counter per 128 B)
+    double *partials;                   // [ngroups][2][ctas_per_group]
+    int *status;                        // [0]: watchdog flag
+    int ngroups, ctas_per_group;
+    long long spin_limit;               // watchdog, in clock64 ticks
+};
+
+// prep.cu
+cudaError_t launch_setup(int *minmax_slots, int npairs, unsigned *bar, int nbar, int *status, cudaStream_t st);
+cudaError_t launch_minmax(const float *const *I0, const float *const *I1, int n, int npairs, int *slots, cudaStream_t st);
+// dst[z] = gaussian(normalise?(src[z])); z < nimg.  Sources come from the device pointer table `srcs` or, when
+// it is null, from src_base + z * src_stride; dst images are dst_base + z * dst_stride.  When slots != null image z is normalised with the min/max of pair z % npairs.
+cudaError_t launch_gauss(const float *const *srcs, const float *src_base, long long src_stride, float *dst_base,
+                         long long dst_stride, int nx, int ny, int nimg, const GaussTaps &taps, const int *slots,
+                         int npairs, cudaStream_t st);
+cudaError_t launch_resample(const float *src_base, long long src_stride, int nx, int ny, float *dst_base,
+                            long long dst_stride, int nxx, int nyy, float fx, float fy, int nimg, cudaStream_t st);
+cudaError_t launch_gray(const float *img, float *gray, long long npix_total, int c, cudaStream_t st);
+
+// solver.cu
+cudaError_t solver_max_ctas(int *ctas_per_sm, int *sms);
+cudaError_t launch_solver(const SolverArgs &args, cudaStream_t st);
+int solver_threads();
+
+// warp.cu
+struct WarpArgs {
+    const float *x;
+    const float *flow;
+    float *out;
+    float *mask;                        // nullable, [B][1][H][W]
+    int B, C, H, W;
+    long long xs_b, xs_c, xs_h, xs_w;   // element strides of x
+    long long os_b, os_c, os_h, os_w;   // element strides of out
+    int fh, fw;                         // flow grid; (H, W) or (H/2, W/2) with fused upsample_factor_2
+    float flow_mul;
+    int interp;                         // 0 bilinear, 1 bicubic
+};
+cudaError_t launch_warp(const WarpArgs &a, cudaStream_t st);
+cudaError_t launch_upsample2(const float *in, float *out, long long planes, int h, int w, float mul, cudaStream_t st);
+
+}  // namespace rvdd

@@ -1,0 +1,244 @@
+// solver_core.h -- the per-lane math of the persistent solver (solver.cu), written as host/device code so the
+// very same functions can be compiled by g++ and checked bit for bit against the oracle on a machine without
+// a GPU (tests/hostsim/).  On the device RVDD_HD is __host__ __device__ __forceinline__.
+#pragma once
+#include "exact_math.h"
+
+namespace rvdd {
+
+// ------------------------------------------------------------------------------------------------ vectors
+
+template <int V> struct Vec;
+template <> struct Vec<4> {
+    RVDD_HDM void ld(const float *p, float (&v)[4])
+    {
+#if defined(__CUDA_ARCH__)
+        const float4 t = *reinterpret_cast<const float4 *>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+#else
+        v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; v[3] = p[3];
+#endif
+    }
+    RVDD_HDM void st(float *p, const float (&v)[4])
+    {
+#if defined(__CUDA_ARCH__)
+        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+#else
+        p[0] = v[0]; p[1] = v[1]; p[2] = v[2]; p[3] = v[3];
+#endif
+    }
+};
+template <> struct Vec<1> {
+    RVDD_HDM void ld(const float *p, float (&v)[1]) { v[0] = *p; }
+    RVDD_HDM void st(float *p, const float (&v)[1]) { *p = v[0]; }
+};
+
+struct IterPtrs {
+    const float *u1, *u2, *p11, *p12, *p21, *p22;       // read buffers
+    float *nu1, *nu2, *np11, *np12, *np21, *np22;       // write buffers
+    const float *gx, *gy, *g2, *rc;                     // per-warp constants
+};
+
+// What one lane carries for one image row: the NEW flow at its V pixels plus the right neighbour, the OLD dual
+// variable, and the residual terms.
+template <int V> struct RowState {
+    float n1[V + 1], n2[V + 1];
+    float p11[V], p21[V];
+    float p12[V + 1], p22[V + 1];
+    float res[V];
+};
+
+// Load row y at columns x0..x0+V (the extra column only if it exists) and run TH + primal update there.
+// up12 / up22: p12 / p22 of row y-1 at the same V+1 columns (ignored when y == 0).
+template <int V>
+RVDD_HD void eval_row(const IterPtrs &P, int x0, int y, int nx, int ny, float l_t, float theta,
+                                         const float (&up12)[V + 1], const float (&up22)[V + 1], RowState<V> &R)
+{
+    const long long base = (long long)y * nx + x0;
+    const bool right = (x0 + V < nx);
+    float u1[V + 1], u2[V + 1], gx[V + 1], gy[V + 1], g2[V + 1], rc[V + 1], a11[V + 1], a21[V + 1];
+    {
+        float t[V];
+        Vec<V>::ld(P.u1 + base, t);
+#pragma unroll
+        for (int j = 0; j < V; j++) u1[j] = t[j];
+        Vec<V>::ld(P.u2 + base, t);
+#pragma unroll
+        for (int j = 0; j < V; j++) u2[j] = t[j];
+        Vec<V>::ld(P.gx + base, t);
+#pragma unroll
+        for (int j = 0; j < V; j++) gx[j] = t[j];
+        Vec<V>::ld(P.gy + base, t);
+#pragma unroll
+        for (int j = 0; j < V; j++) gy[j] = t[j];
+        Vec<V>::ld(P.g2 + base, t);
+#pragma unroll
+        for (int j = 0; j < V; j++) g2[j] = t[j];
+        Vec<V>::ld(P.rc + base, t);
+#pragma unroll
+        for (int j = 0; j < V; j++) rc[j] = t[j];
+        Vec<V>::ld(P.p11 + base, t);
+#pragma unroll
+        for (int j = 0; j < V; j++) a11[j] = t[j];
+        Vec<V>::ld(P.p21 + base, t);
+#pragma unroll
+        for (int j = 0; j < V; j++) a21[j] = t[j];
+        Vec<V>::ld(P.p12 + base, t);
+#pragma unroll
+        for (int j = 0; j < V; j++) R.p12[j] = t[j];
+        Vec<V>::ld(P.p22 + base, t);
+#pragma unroll
+        for (int j = 0; j < V; j++) R.p22[j] = t[j];
+    }
+    u1[V] = u2[V] = gx[V] = gy[V] = g2[V] = rc[V] = a11[V] = a21[V] = 0.f;
+    R.p12[V] = R.p22[V] = 0.f;
+    if (right) {
+        const long long q = base + V;
+        u1[V] = P.u1[q]; u2[V] = P.u2[q]; gx[V] = P.gx[q]; gy[V] = P.gy[q]; g2[V] = P.g2[q]; rc[V] = P.rc[q];
+        a11[V] = P.p11[q]; a21[V] = P.p21[q]; R.p12[V] = P.p12[q]; R.p22[V] = P.p22[q];
+    }
+    float l11 = 0.f, l21 = 0.f;
+    if (x0 > 0) { l11 = P.p11[base - 1]; l21 = P.p21[base - 1]; }
+#pragma unroll
+    for (int j = 0; j <= V; j++) {
+        if (j == V && !right) break;
+        const int x = x0 + j;
+        const float d1 = rvdd_div_px(a11[j], j ? a11[j - 1] : l11, R.p12[j], up12[j], x, y, nx, ny);
+        const float d2 = rvdd_div_px(a21[j], j ? a21[j - 1] : l21, R.p22[j], up22[j], x, y, nx, ny);
+        rvdd_primal_px(u1[j], u2[j], gx[j], gy[j], g2[j], rc[j], d1, d2, l_t, theta, &R.n1[j], &R.n2[j]);
+    }
+    if (!right) { R.n1[V] = 0.f; R.n2[V] = 0.f; }
+#pragma unroll
+    for (int j = 0; j < V; j++) {
+        R.p11[j] = a11[j];
+        R.p21[j] = a21[j];
+        R.res[j] = rvdd_residual_px(R.n1[j], u1[j], R.n2[j], u2[j]);
+    }
+}
+
+// One lane's strip: columns x0..x0+V-1, rows y0..y1-1.  Returns the residual sum of those pixels.
+template <int V>
+RVDD_HD double iterate_strip(const IterPtrs &P, int x0, int y0, int y1, int nx, int ny, float l_t,
+                                                float theta, float taut)
+{
+    double err = 0.0;
+    float up12[V + 1], up22[V + 1];
+#pragma unroll
+    for (int j = 0; j <= V; j++) up12[j] = up22[j] = 0.f;
+    if (y0 > 0) {
+        const long long b = (long long)(y0 - 1) * nx + x0;
+        float t[V];
+        Vec<V>::ld(P.p12 + b, t);
+#pragma unroll
+        for (int j = 0; j < V; j++) up12[j] = t[j];
+        Vec<V>::ld(P.p22 + b, t);
+#pragma unroll
+        for (int j = 0; j < V; j++) up22[j] = t[j];
+        if (x0 + V < nx) { up12[V] = P.p12[b + V]; up22[V] = P.p22[b + V]; }
+    }
+    RowState<V> cur, nxt;
+    eval_row<V>(P, x0, y0, nx, ny, l_t, theta, up12, up22, cur);
+    for (int y = y0; y < y1; y++) {
+        const bool down = (y + 1 < ny);
+        if (down) eval_row<V>(P, x0, y + 1, nx, ny, l_t, theta, cur.p12, cur.p22, nxt);
+        float o11[V], o12[V], o21[V], o22[V], o1[V], o2[V];
+#pragma unroll
+        for (int j = 0; j < V; j++) {
+            const int x = x0 + j;
+            // forward differences of the NEW flow (mask.c:98-141): zero on the last column / row
+            const float u1x = (x < nx - 1) ? FSUB(cur.n1[j + 1], cur.n1[j]) : 0.f;
+            const float u2x = (x < nx - 1) ? FSUB(cur.n2[j + 1], cur.n2[j]) : 0.f;
+            const float u1y = down ? FSUB(nxt.n1[j], cur.n1[j]) : 0.f;
+            const float u2y = down ? FSUB(nxt.n2[j], cur.n2[j]) : 0.f;
+            o11[j] = cur.p11[j]; o12[j] = cur.p12[j]; o21[j] = cur.p21[j]; o22[j] = cur.p22[j];
+            rvdd_dual_px(&o11[j], &o12[j], u1x, u1y, taut);
+            rvdd_dual_px(&o21[j], &o22[j], u2x, u2y, taut);
+            o1[j] = cur.n1[j]; o2[j] = cur.n2[j];
+            err += (double)cur.res[j];
+        }
+        const long long base = (long long)y * nx + x0;
+        Vec<V>::st(P.nu1 + base, o1);
+        Vec<V>::st(P.nu2 + base, o2);
+        Vec<V>::st(P.np11 + base, o11);
+        Vec<V>::st(P.np12 + base, o12);
+        Vec<V>::st(P.np21 + base, o21);
+        Vec<V>::st(P.np22 + base, o22);
+        if (down) cur = nxt;
+    }
+    return err;
+}
+
+
+// ------------------------------------------------------------------------------------------------ per-pixel phases
+
+// centred gradient of I1 at pixel i = (x, y) (tvl1flow_lib.c:131, mask.c:149-206)
+RVDD_HD void cgrad_px(const float *I1, int x, int y, int nx, int ny, float *dx, float *dy)
+{
+    const long long i = (long long)y * nx + x;
+    const float c = I1[i];
+    const float xl = x > 0 ? I1[i - 1] : c, xr = x < nx - 1 ? I1[i + 1] : c;
+    const float yu = y > 0 ? I1[i - nx] : c, yd = y < ny - 1 ? I1[i + nx] : c;
+    *dx = rvdd_half_diff(xr, xl);
+    *dy = rvdd_half_diff(yd, yu);
+}
+
+// per-warp constants at pixel (x, y) (tvl1flow_lib.c:143-159): bicubic samples of I1, I1x, I1y at (x+u1, y+u2)
+// with border_out = true, then |grad|^2 and the constant part of rho.
+RVDD_HD void warp_consts_px(const float *I0, const float *I1, const float *I1x, const float *I1y, float a, float b,
+                            int x, int y, int nx, int ny, float *gx, float *gy, float *g2, float *rc)
+{
+    const float uu = FADD((float)x, a), vv = FADD((float)y, b);
+    float w0 = 0.f, wx = 0.f, wy = 0.f;
+    if (rvdd_inside_strict(uu, vv, nx, ny)) {
+        const int bx = (int)uu, by = (int)vv;
+        const float tx = FSUB(uu, (float)bx), ty = FSUB(vv, (float)by);
+        const long long o = (long long)(by - 1) * nx + (bx - 1);
+        float v[4][4];
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) v[c][r] = I1[o + r * nx + c];
+        w0 = rvdd_bicubic_cell(v, tx, ty);
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) v[c][r] = I1x[o + r * nx + c];
+        wx = rvdd_bicubic_cell(v, tx, ty);
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) v[c][r] = I1y[o + r * nx + c];
+        wy = rvdd_bicubic_cell(v, tx, ty);
+    }
+    *gx = wx;
+    *gy = wy;
+    *g2 = FADD(FMUL(wx, wx), FMUL(wy, wy));
+    *rc = FSUB(FSUB(FSUB(w0, FMUL(wx, a)), FMUL(wy, b)), I0[(long long)y * nx + x]);
+}
+
+// flow upsampling to the next finer level at fine pixel (x, y) (zoom.c:85-109 + tvl1flow_lib.c:431-432)
+RVDD_HD float zoom_in_px(const float *coarse, int x, int y, int nx, int ny, float zx, float zy, float mul)
+{
+    return FMUL(rvdd_bicubic_clamped(coarse, FDIV((float)x, zx), FDIV((float)y, zy), nx, ny), mul);
+}
+
+// strip decomposition of an nx*ny image over `nwarps` warps with V pixels per lane: column segments of 32*V
+// pixels, `rows` rows per strip.
+struct StripPlan {
+    int ncol, rows, nstrips, total;
+};
+template <int V> RVDD_HD StripPlan plan_strips(int nx, int ny, int nwarps)
+{
+    StripPlan p;
+    const int segw = 32 * V;
+    p.ncol = (nx + segw - 1) / segw;
+    int per_col = nwarps / p.ncol;
+    if (per_col < 1) per_col = 1;
+    p.rows = (ny + per_col - 1) / per_col;
+    if (p.rows < 1) p.rows = 1;
+    p.nstrips = (ny + p.rows - 1) / p.rows;
+    p.total = p.ncol * p.nstrips;
+    return p;
+}
+
+}  // namespace rvdd

@@ -1,0 +1,152 @@
+// warp.cu -- flow-based backward warp of multi-channel tensors, the CUDA side of util/flow_utils.py:
+//   warp(x, flow, interp)            (flow_utils.py:70-102)  -> grid_sample(bicubic|bilinear, border, align_corners)
+//   upsample_factor_2(t, multiply)   (flow_utils.py:159-174) -> bilinear x2, align_corners, optionally fused
+// One thread owns one output pixel: the sampling position, the 16 tap offsets and the 8 cubic weights are
+// computed once from the flow and reused for every channel, so a C-channel warp reads the flow once instead
+// of once per channel, rebuilds no meshgrid, and writes the validity mask in the same pass (no D2H sync).
+//
+// Semantics follow ATen's grid_sampler_2d (float32): normalise 2*v/(W-1)-1 as flow_utils.py:93-94 does,
+// un-normalise ((g+1)/2)*(W-1), bicubic = Keys A=-0.75 with the centre left unclipped and every tap clamped to
+// the image, bilinear = centre clipped to the border first.  Results agree with torch to ~1e-6 relative (the
+// float expression order of the two ATen back ends differs by that much already); the gate is 1e-4.
+#include "internal.h"
+
+namespace rvdd {
+
+__device__ __forceinline__ void cubic_coeffs(float t, float (&c)[4])
+{
+    const float A = -0.75f;
+    float x = t + 1.0f;
+    c[0] = ((A * x - 5.0f * A) * x + 8.0f * A) * x - 4.0f * A;
+    x = t;
+    c[1] = ((A + 2.0f) * x - (A + 3.0f)) * x * x + 1.0f;
+    x = 1.0f - t;
+    c[2] = ((A + 2.0f) * x - (A + 3.0f)) * x * x + 1.0f;
+    x = 2.0f - t;
+    c[3] = ((A * x - 5.0f * A) * x + 8.0f * A) * x - 4.0f * A;
+}
+
+// bilinear x2 upsampling with align_corners=True (ATen upsample_bilinear2d): src = dst * (in-1)/(out-1)
+__device__ __forceinline__ float up2_sample(const float *__restrict__ p, int h, int w, int y, int x, float sy, float sx)
+{
+    const float fy = sy * (float)y, fx = sx * (float)x;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float hy = 1.0f - ly, hx = 1.0f - lx;
+    return hy * (hx * p[(long long)y0 * w + x0] + lx * p[(long long)y0 * w + x1]) +
+           ly * (hx * p[(long long)y1 * w + x0] + lx * p[(long long)y1 * w + x1]);
+}
+
+template <int INTERP>
+__global__ void __launch_bounds__(256) warp_kernel(const WarpArgs a)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int b = blockIdx.z;
+    if (x >= a.W || y >= a.H) return;
+
+    // flow at this pixel (optionally bilinearly upsampled from the half-resolution grid and scaled)
+    float fu, fv;
+    const float *fl = a.flow + (long long)b * 2 * a.fh * a.fw;
+    if (a.fh == a.H && a.fw == a.W) {
+        fu = fl[(long long)y * a.W + x];
+        fv = fl[(long long)a.H * a.W + (long long)y * a.W + x];
+    } else {
+        const float sy = a.H > 1 ? (float)(a.fh - 1) / (float)(a.H - 1) : 0.f;
+        const float sx = a.W > 1 ? (float)(a.fw - 1) / (float)(a.W - 1) : 0.f;
+        fu = up2_sample(fl, a.fh, a.fw, y, x, sy, sx);
+        fv = up2_sample(fl + (long long)a.fh * a.fw, a.fh, a.fw, y, x, sy, sx);
+    }
+    fu *= a.flow_mul;
+    fv *= a.flow_mul;
+
+    // flow_utils.py:90-96: vgrid, normalisation, validity mask
+    const float gxn = 2.0f * ((float)x + fu) / (float)(a.W - 1) - 1.0f;
+    const float gyn = 2.0f * ((float)y + fv) / (float)(a.H - 1) - 1.0f;
+    if (a.mask)
+        a.mask[((long long)b * a.H + y) * a.W + x] = (gxn >= -1.f && gxn <= 1.f && gyn >= -1.f && gyn <= 1.f) ? 1.f : 0.f;
+    // grid_sampler_unnormalize, align_corners=True
+    float ix = ((gxn + 1.f) / 2.f) * (float)(a.W - 1);
+    float iy = ((gyn + 1.f) / 2.f) * (float)(a.H - 1);
+
+    const float *xb = a.x + (long long)b * a.xs_b;
+    float *ob = a.out + (long long)b * a.os_b + (long long)y * a.os_h + (long long)x * a.os_w;
+
+    if (INTERP == 1) {
+        const float fx0 = floorf(ix), fy0 = floorf(iy);
+        float cx[4], cy[4];
+        cubic_coeffs(ix - fx0, cx);
+        cubic_coeffs(iy - fy0, cy);
+        long long ox[4], oy[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            // get_value_bounded: clip the float tap coordinate to [0, size-1], then truncate
+            const float tx = fminf((float)(a.W - 1), fmaxf(fx0 - 1.f + (float)k, 0.f));
+            const float ty = fminf((float)(a.H - 1), fmaxf(fy0 - 1.f + (float)k, 0.f));
+            ox[k] = (long long)(int)tx * a.xs_w;
+            oy[k] = (long long)(int)ty * a.xs_h;
+        }
+        for (int c = 0; c < a.C; c++) {
+            const float *p = xb + (long long)c * a.xs_c;
+            float acc = 0.f;
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const float *q = p + oy[r];
+                const float row = __ldg(q + ox[0]) * cx[0] + __ldg(q + ox[1]) * cx[1] + __ldg(q + ox[2]) * cx[2] +
+                                  __ldg(q + ox[3]) * cx[3];
+                acc += row * cy[r];
+            }
+            ob[(long long)c * a.os_c] = acc;
+        }
+    } else {
+        // bilinear, padding border: clip the centre, then the usual 4 taps (out-of-range taps have weight 0)
+        ix = fminf((float)(a.W - 1), fmaxf(ix, 0.f));
+        iy = fminf((float)(a.H - 1), fmaxf(iy, 0.f));
+        const float fx0 = floorf(ix), fy0 = floorf(iy);
+        const int x0 = (int)fx0, y0 = (int)fy0;
+        const int x1 = min(x0 + 1, a.W - 1), y1 = min(y0 + 1, a.H - 1);
+        const float lx = ix - fx0, ly = iy - fy0;
+        const float wnw = (1.f - lx) * (1.f - ly), wne = lx * (1.f - ly), wsw = (1.f - lx) * ly, wse = lx * ly;
+        for (int c = 0; c < a.C; c++) {
+            const float *p = xb + (long long)c * a.xs_c;
+            ob[(long long)c * a.os_c] = __ldg(p + (long long)y0 * a.xs_h + (long long)x0 * a.xs_w) * wnw +
+                                        __ldg(p + (long long)y0 * a.xs_h + (long long)x1 * a.xs_w) * wne +
+                                        __ldg(p + (long long)y1 * a.xs_h + (long long)x0 * a.xs_w) * wsw +
+                                        __ldg(p + (long long)y1 * a.xs_h + (long long)x1 * a.xs_w) * wse;
+        }
+    }
+}
+
+cudaError_t launch_warp(const WarpArgs &a, cudaStream_t st)
+{
+    if (a.B <= 0 || a.C <= 0 || a.H <= 0 || a.W <= 0) return cudaSuccess;
+    dim3 grid((a.W + 31) / 32, (a.H + 7) / 8, a.B);
+    if (a.interp == 1)
+        warp_kernel<1><<<grid, 256, 0, st>>>(a);
+    else
+        warp_kernel<0><<<grid, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+__global__ void upsample2_kernel(const float *__restrict__ in, float *__restrict__ out, int h, int w, float mul)
+{
+    const int H = 2 * h, W = 2 * w;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    const float sy = (float)(h - 1) / (float)(H - 1), sx = (float)(w - 1) / (float)(W - 1);
+    const float *p = in + (long long)blockIdx.z * h * w;
+    out[((long long)blockIdx.z * H + y) * W + x] = up2_sample(p, h, w, y, x, sy, sx) * mul;
+}
+
+cudaError_t launch_upsample2(const float *in, float *out, long long planes, int h, int w, float mul, cudaStream_t st)
+{
+    if (planes <= 0) return cudaSuccess;
+    if (planes > 65535) return cudaErrorInvalidValue;
+    dim3 grid((2 * w + 31) / 32, (2 * h + 7) / 8, (unsigned)planes);
+    upsample2_kernel<<<grid, 256, 0, st>>>(in, out, h, w, mul);
+    return cudaGetLastError();
+}
+
+}  // namespace rvdd

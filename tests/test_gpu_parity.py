@@ -1,0 +1,194 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI of libBridge.so, against the oracle on the same seeded
+inputs.  Integer-like quantities (iteration counts per scale and warp) must coincide; float results are compared
+bit for bit where the arithmetic is rounding-exact by construction and with the north-star tolerances otherwise
+(mean end-point error <= 0.01 px for flows, <= 1e-4 relative for warped pixels)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import warp_ref
+from rvdd_release_b200 import synth
+
+pytestmark = pytest.mark.gpu
+EPE_TOL = 0.01          # px, BASELINE.json north_star
+WARP_RTOL = 1e-4        # relative, BASELINE.json north_star
+
+
+def epe(a, b):
+    return float(np.sqrt(((a - b) ** 2).sum(axis=-3)).mean())
+
+
+def run_pairs(bridge, pairs, groups=0, trace=True):
+    """pairs: list of (I0, I1) numpy gray images of one size -> flows [k,2,h,w], iters [k,S,5]."""
+    k = len(pairs)
+    gray = torch.from_numpy(np.stack([im for pr in pairs for im in pr])).cuda()
+    tgt, src = np.arange(0, 2 * k, 2), np.arange(1, 2 * k, 2)
+    bridge.set_groups(groups)
+    flow, iters = bridge.tvl1_flow(gray, src, tgt, trace=True, check=True)
+    bridge.set_groups(0)
+    S = len(bridge.pyramid(gray.shape[2], gray.shape[1]))
+    return flow.cpu().numpy(), iters.cpu().numpy()[:, :S, :]
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "tvl1_*.npz"))))
+def test_flow_matches_reference_golden(bridge, port, path):
+    g = np.load(path)
+    flow, iters = run_pairs(bridge, [(g["I0"], g["I1"])])
+    _, it_ref, _, _, _ = port.tvl1flow_traced(g["I0"], g["I1"], err_mode=0)
+    assert np.array_equal(iters[0], it_ref), (iters[0], it_ref)
+    assert epe(flow[0], g["flow"]) <= EPE_TOL
+    assert np.array_equal(flow[0], g["flow"])       # rounding-exact arithmetic: identical bits
+
+
+def test_pyramid_levels_bit_exact(bridge, port):
+    I0, I1 = synth.gray_pair(90, 160, "iso3200")
+    run_pairs(bridge, [(I0, I1)])
+    a, b = port.normalize(I0, I1)
+    a, b = port.gaussian(a, 0.8), port.gaussian(b, 0.8)
+    for lvl, (nx, ny) in enumerate(bridge.pyramid(160, 90)):
+        assert np.array_equal(bridge.debug_level(0, 0, lvl, nx, ny).cpu().numpy(), a), lvl
+        assert np.array_equal(bridge.debug_level(0, 1, lvl, nx, ny).cpu().numpy(), b), lvl
+        a, b = port.zoom_out(a), port.zoom_out(b)
+
+
+@pytest.mark.parametrize("h,w,iso", [(97, 131, "iso12800"), (180, 320, "iso3200"), (135, 240, "clean"), (64, 260, "iso3200")])
+def test_flow_various_sizes(bridge, port, h, w, iso):
+    I0, I1 = synth.gray_pair(h, w, iso)
+    ref, it_ref, _, _, _ = port.tvl1flow_traced(I0, I1, err_mode=0)
+    flow, iters = run_pairs(bridge, [(I0, I1)])
+    assert np.array_equal(iters[0], it_ref)
+    assert epe(flow[0], ref) <= EPE_TOL
+    assert np.array_equal(flow[0], ref)
+
+
+def test_batch_groups_and_determinism(bridge, port):
+    """A batch of different pairs gives the same bits whatever the number of solver groups, and twice in a row."""
+    seq = synth.sequence(6, 90, 160, "iso3200").numpy().mean(axis=3, dtype=np.float32)
+    pairs = [(seq[t], seq[t - 1]) for t in range(1, 6)] + [(seq[t], seq[t + 1]) for t in range(0, 3)]
+    refs = [port.tvl1flow_traced(a, b, err_mode=0) for a, b in pairs]
+    base = None
+    for groups in (1, 3, 8, 0):
+        flow, iters = run_pairs(bridge, pairs, groups=groups)
+        if base is None:
+            base = flow
+        assert np.array_equal(flow, base), groups
+        for k, r in enumerate(refs):
+            assert np.array_equal(iters[k], r[1]), (groups, k)
+            assert epe(flow[k], r[0]) <= EPE_TOL
+    flow2, _ = run_pairs(bridge, pairs, groups=8)
+    assert np.array_equal(flow2, base)
+
+
+def test_flow_1280x720_against_oracle(bridge, port):
+    """The headline geometry: one noisy 1280x720 pair, 7 scales, against the oracle (a few seconds of CPU)."""
+    I0, I1 = synth.gray_pair(720, 1280, "iso3200")
+    ref, it_ref, _, _, _ = port.tvl1flow_traced(I0, I1, err_mode=0)
+    flow, iters = run_pairs(bridge, [(I0, I1)])
+    assert iters.shape[1] == 7
+    mism = int((iters[0] != it_ref).sum())
+    e = epe(flow[0], ref)
+    print("1280x720: EPE %.6f px, iteration-count mismatches %d, iters/scale %s" % (e, mism, iters[0].sum(1).tolist()))
+    assert e <= EPE_TOL
+    assert mism == 0 and np.array_equal(flow[0], ref)
+
+
+def test_zero_motion_and_linearity_properties(bridge):
+    """Size-independent properties at full size: identical frames give exactly zero flow; the flow of a pair does
+    not depend on what else is in the batch."""
+    I0, _ = synth.gray_pair(720, 1280, "iso3200")
+    J0, J1 = synth.gray_pair(720, 1280, "iso12800", t=2)
+    flow, _ = run_pairs(bridge, [(I0, I0), (J0, J1)])
+    assert np.count_nonzero(flow[0]) == 0
+    solo, _ = run_pairs(bridge, [(J0, J1)])
+    assert np.array_equal(solo[0], flow[1])
+
+
+def test_dropin_cppbridge_host_call(libpath, bridge, port):
+    """library.CPPbridge(libpath).TVL1_flow(Im1, Im2) with numpy HWC inputs, exactly as the reference is used."""
+    from rvdd_release_b200.library import CPPbridge
+    seq = synth.sequence(2, 72, 128, "iso3200").numpy()
+    flow = CPPbridge(libpath).TVL1_flow(seq[1], seq[0])
+    assert flow.shape == (72, 128, 2) and flow.dtype == np.float32
+    ref = port.tvl1flow(np.mean(seq[1], axis=2), np.mean(seq[0], axis=2))
+    assert np.array_equal(flow.transpose(2, 0, 1), ref)
+
+
+def test_gray_kernel_matches_numpy(bridge):
+    seq = synth.sequence(3, 40, 64, "iso12800")
+    g = bridge.gray(seq.cuda()).cpu().numpy()
+    assert np.array_equal(g, np.mean(seq.numpy(), axis=3))
+
+
+# ------------------------------------------------------------------------------------------------ warp
+
+def rel_err(a, b):
+    return float(np.abs(a - b).max() / max(1e-12, np.abs(b).max()))
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "warp_*.npz"))))
+def test_warp_matches_reference_golden(bridge, path):
+    from rvdd_release_b200 import flow_utils
+    g = np.load(path)
+    x, flow = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["flow"]).cuda()
+    yb, m = flow_utils.warp(x, flow, "bicubic")
+    yl, _ = flow_utils.warp(x, flow, "bilinear")
+    assert rel_err(yb.cpu().numpy(), g["bicubic"]) <= WARP_RTOL
+    assert rel_err(yl.cpu().numpy(), g["bilinear"]) <= WARP_RTOL
+    assert np.array_equal(m.cpu().numpy(), g["mask"]) and m.device == x.device
+    up = flow_utils.upsample_factor_2(torch.from_numpy(g["half_flow"]).cuda(), 2)
+    assert rel_err(up.cpu().numpy(), g["up2x2"]) <= WARP_RTOL
+    # fused x2 upsampling of a half-resolution flow inside the warp (recurrent_model.py:129 + :151)
+    yh, _ = flow_utils.warp(x, torch.from_numpy(g["half_flow"]).cuda(), "bicubic", flow_mul=2.0)
+    assert rel_err(yh.cpu().numpy(), g["bicubic_half"]) <= 5 * WARP_RTOL
+
+
+@pytest.mark.parametrize("C,H,W", [(3, 720, 1280), (48, 180, 320), (4, 360, 640)])
+def test_warp_against_oracle_sizes(bridge, C, H, W):
+    from rvdd_release_b200 import flow_utils
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(1, C, H, W, generator=g)
+    flow = 4.0 * torch.randn(1, 2, H, W, generator=g)
+    ref, mref = warp_ref.warp(x, flow, "bicubic")
+    y, m = flow_utils.warp(x.cuda(), flow.cuda(), "bicubic")
+    assert rel_err(y.cpu().numpy(), ref.numpy()) <= WARP_RTOL
+    assert np.array_equal(m.cpu().numpy(), mref.numpy())
+
+
+def test_warp_channel_slice_and_identity(bridge):
+    """The feature-recurrence call site warps a channel slice of a bigger tensor (recurrent_model.py:295-297);
+    zero flow is the identity (cubic weights are exactly (0, 1, 0, 0) at t = 0)."""
+    from rvdd_release_b200 import flow_utils
+    g = torch.Generator().manual_seed(7)
+    feat = torch.randn(2, 96, 36, 52, generator=g).cuda()
+    flow = (3.0 * torch.randn(2, 2, 36, 52, generator=g)).cuda()
+    sl = feat[:, 48:96]
+    y, _ = flow_utils.warp(sl, flow, "bicubic")
+    ref, _ = warp_ref.warp(sl.cpu().contiguous(), flow.cpu(), "bicubic")
+    assert rel_err(y.cpu().numpy(), ref.numpy()) <= WARP_RTOL
+    ident, m = flow_utils.warp(sl, torch.zeros_like(flow), "bicubic")
+    assert torch.equal(ident, sl.contiguous()) and bool((m == 1).all())
+    with pytest.raises(Exception):
+        flow_utils.warp(sl.cpu(), flow.cpu(), "bicubic")            # no CPU fallback
+
+
+def test_single_warp_and_compute_flow_and_warp(libpath, bridge, port):
+    """numpy-level API of util/flow_utils.py:105-156 and the host-buffer batch entry point."""
+    from rvdd_release_b200 import flow_utils
+    seq = synth.sequence(3, 72, 128, "iso3200").numpy()
+    warped, mask, flow = flow_utils.compute_flow_and_warp(seq[0], seq[1])          # img1 = source, img2 = target
+    ref_flow = port.tvl1flow(np.mean(seq[1], axis=2), np.mean(seq[0], axis=2)).transpose(1, 2, 0)
+    assert np.array_equal(flow, ref_flow)
+    ref_w, _ = warp_ref.warp(torch.from_numpy(seq[0].transpose(2, 0, 1)[None].copy()),
+                             torch.from_numpy(ref_flow.transpose(2, 0, 1)[None].copy()), "bicubic")
+    assert rel_err(warped, ref_w[0].numpy().transpose(1, 2, 0)) <= WARP_RTOL
+    # batch, host buffers in / out
+    f, w, it = bridge.flow_and_warp_host(seq, src=[0, 2], tgt=[1, 1], trace=True)
+    assert np.array_equal(f[0].numpy(), ref_flow)
+    assert rel_err(w[0].numpy(), ref_w[0].numpy().transpose(1, 2, 0)) <= WARP_RTOL
+    ref2 = port.tvl1flow(np.mean(seq[1], axis=2), np.mean(seq[2], axis=2)).transpose(1, 2, 0)
+    assert np.array_equal(f[1].numpy(), ref2)
+    assert int(it[0].sum()) > 0

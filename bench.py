@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- flow+warp pairs/s @1280x720 (BASELINE.json metric) on N B200s of one node.
+
+A "step" is one 30-frame synthetic 1280x720x4 packed-raw sequence (ISO 3200 noise): mean-of-4 gray of every frame,
+TV-L1 flow t-1 -> t for the 29 consecutive pairs (default parameters, 7 scales) and the bicubic backward warp of
+each 4-channel source frame by its flow -- 29 x `compute_flow_and_warp` (data/base_dataset.py:178 in the
+reference), the unit SURVEY.md section 8d defines.  One process per GPU, every rank works on its own sequence
+(weak scaling, no collective on the data path; torch.distributed is only the barrier and the max over ranks).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference C TV-L1 + torch-CPU warp on the host cores
+
+Prints ONE JSON line (rank 0).  `value` is timed with CUDA events with the frames resident in HBM; `e2e` is the same
+metric through the host-buffer C-ABI call (pinned host frames in, flows + warped frames out, copies inside the
+timed region); `roofline` is the persistent solver kernel's algorithmic bytes (from the measured iteration counts)
+over its event-timed duration against MEASURED_PEAKS.json; `cpu_baseline` is the reference C timed on this box.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, CH, NFRAMES = 720, 1280, 4, 30
+ISO = "iso3200"
+METRIC = "flow+warp pairs/s @1280x720"
+WORKLOAD = ("configs[1]: 30-frame synthetic 1280x720x4 packed-raw sequence (ISO 3200 noise), TV-L1 flow t-1->t + "
+            "bicubic warp of the 4-ch source frame, 29 pairs per step, default TV-L1 parameters (7 scales, 5 warps)")
+FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def finish(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def solver_bytes(sizes, iters, nwarps=5):
+    """Algorithmic bytes of one solver launch: per pair and scale 3N (centred gradient) +
+    10N per warp (bicubic warp constants) + 16N per inner iteration (64 B/pixel) + 2(N_s + N_{s-1}) flow upsampling,
+    times 4 bytes.  iters: [pairs, S, nwarps] measured counts."""
+    total = 0
+    for k in range(iters.shape[0]):
+        for s, (nx, ny) in enumerate(sizes):
+            n = nx * ny
+            total += 3 * n + nwarps * 10 * n + 16 * n * int(iters[k, s].sum())
+            if s > 0:
+                total += 2 * (n + sizes[s - 1][0] * sizes[s - 1][1])
+        total += 2 * sizes[0][0] * sizes[0][1] * 2      # final flow copy-out (read + write 2N)
+    return 4 * total
+
+
+def step_bytes(sizes, iters, nwarps=5):
+    """Whole-step algorithmic bytes: solver + gray prepass + pyramid + final 4-channel warp (section 8d)."""
+    n0 = sizes[0][0] * sizes[0][1]
+    k = iters.shape[0]
+    fixed = 6 * n0 + sum(2 * (sizes[s - 1][0] * sizes[s - 1][1] + sizes[s][0] * sizes[s][1]) for s in range(1, len(sizes)))
+    gray = NFRAMES * (CH + 1) * n0
+    warp = k * (2 * CH + 2) * n0
+    return solver_bytes(sizes, iters, nwarps) + 4 * (k * fixed + gray + warp)
+
+
+def cpu_reference(frames_np, pairs, threads):
+    """Reference CPU path on `pairs` (list of (src, tgt)): numpy mean-of-4 gray, reference C tvl1flow
+    (oracle/_ref, OpenMP) or the oracle port when the compiled reference is absent, torch-CPU grid_sample warp.
+    Returns (seconds, kind)."""
+    import torch
+    from oracle import warp_ref
+    from oracle.oracle import PortLib, RefLib
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    try:
+        lib, kind = RefLib("omp"), "reference"
+    except Exception:
+        lib, kind = PortLib(), "port"
+    torch.set_num_threads(threads)
+    t0 = time.perf_counter()
+    for s, t in pairs:
+        i0 = np.ascontiguousarray(np.mean(frames_np[t], axis=2))
+        i1 = np.ascontiguousarray(np.mean(frames_np[s], axis=2))
+        flow = lib.tvl1flow(i0, i1)
+        x = torch.from_numpy(np.ascontiguousarray(frames_np[s].transpose(2, 0, 1))[None])
+        warp_ref.warp(x, torch.from_numpy(flow[None]), "bicubic")
+    return time.perf_counter() - t0, kind
+
+
+# ------------------------------------------------------------------------------------------------ arms
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation on this box's host cores, rank 0 only."""
+    if rank != 0:
+        return
+    import torch
+    from rvdd_release_b200 import synth
+    threads = os.cpu_count() or 1
+    sample_pairs = 2
+    seq = synth.sequence(sample_pairs + 1, H, W, ISO).numpy()
+    pairs = [(t - 1, t) for t in range(1, sample_pairs + 1)]
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference(seq, pairs[:1], threads)
+    steps = max(1, min(args.steps, 5))
+    times, kind = [], "reference"
+    for _ in range(steps):
+        dt, kind = cpu_reference(seq, pairs, threads)
+        times.append(dt)
+    total = sum(times)
+    value = steps * sample_pairs / total
+    sample = "%d pairs per step of the same 1280x720x4 ISO-3200 sequence, %d steps" % (sample_pairs, steps)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from rvdd_release_b200 import bridge as B
+    from rvdd_release_b200 import synth
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    br = B.default_bridge()
+    if args.groups:
+        br.set_groups(args.groups)
+
+    # synthetic input, generated on the device (not timed); every rank gets its own noise realisation
+    frames = synth.sequence(NFRAMES, H, W, ISO, device=dev, noise_seed=1000 * rank)
+    src = np.arange(0, NFRAMES - 1, dtype=np.int32)
+    tgt = np.arange(1, NFRAMES, dtype=np.int32)
+    npairs = len(src)
+    sizes = br.pyramid(W, H)
+    S = len(sizes)
+
+    def step(trace=False):
+        gray = br.gray(frames)
+        out = br.tvl1_flow(gray, src, tgt, trace=trace)
+        flow = out[0] if trace else out
+        x = frames[:npairs].permute(0, 3, 1, 2)                    # source frames t-1 as [29, 4, H, W] views
+        warped, _ = br.warp(x, flow, "bicubic", want_mask=False)
+        return flow, warped, (out[1] if trace else None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    _, _, iters = step(trace=True)
+    br.check(dev)
+    iters = iters.cpu().numpy()[:, :S, :]
+
+    # ---- device-resident timing: K steps, CUDA events on the launching stream, max over ranks
+    br.profile(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.finish()
+    ms = e0.elapsed_time(e1)
+    solver_ms = br.profile_read()
+    br.profile(False)
+    br.check(dev)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * npairs * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call: pinned frames in, flows + warped frames out
+    h_frames = torch.empty((NFRAMES, H, W, CH), dtype=torch.float32).pin_memory()
+    h_frames.copy_(frames.cpu())
+    h_flow = torch.empty((npairs, H, W, 2), dtype=torch.float32).pin_memory()
+    h_warp = torch.empty((npairs, H, W, CH), dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        br.flow_and_warp_host(h_frames, src, tgt, flow_out=h_flow, warped_out=h_warp)
+    e2e_steps = max(1, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        br.flow_and_warp_host(h_frames, src, tgt, flow_out=h_flow, warped_out=h_warp)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * npairs * e2e_steps / e2e_s
+    checksum = float(h_flow.double().abs().mean())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the persistent solver), from the live event timings
+    peak, peak_src = hbm_peak()
+    sb = solver_bytes(sizes, iters)
+    avg_solver_ms = sum(solver_ms) / max(1, len(solver_ms))
+    achieved = sb / (avg_solver_ms * 1e-3) / 1e9 if avg_solver_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "rvdd::solver_kernel (persistent TV-L1 solver, 1 launch per step)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": sb, "avg_launch_ms": avg_solver_ms,
+                "share_of_step": avg_solver_ms * args.steps / ms if ms > 0 else None,
+                "step_algorithmic_bytes": step_bytes(sizes, iters),
+                "step_frac_of_peak": step_bytes(sizes, iters) / (ms / args.steps * 1e-3) / 1e9 / peak}
+
+    # ---- CPU baseline: the reference C on this box's cores, bounded sample of the same workload
+    threads = os.cpu_count() or 1
+    cpu = None
+    if not args.no_cpu_baseline:
+        fr = h_frames[:3].numpy()
+        dt, kind = cpu_reference(fr, [(0, 1), (1, 2)], threads)
+        cpu = {"value": 2 / dt, "unit": "pairs/s", "cores": threads, "kind": kind,
+               "sample": "2 pairs (frames 0-2) of the benchmarked sequence: reference C tvl1flow (OpenMP) + torch-CPU warp"}
+
+    launches_per_step = 1 + (3 + 2 * (S - 1) + 1) + 1     # gray | setup, minmax, presmooth, (gauss, resample)/level, solver | warp
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "pairs_per_step": npairs, "frames": [NFRAMES, H, W, CH], "iso": ISO,
+                   "l2_policy": "inputs larger than L2 (442 MB of frames + >1 GB of solver state per step)",
+                   "solver_groups": args.groups or "auto", "parallelism": "one sequence per GPU, no collective"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h_frames.numel() * 4),
+                "d2h_bytes_per_step": int((h_flow.numel() + h_warp.numel()) * 4), "steps": e2e_steps,
+                "api": "rvdd_flow_and_warp_host (pinned host buffers)"},
+        "gpu_launches": launches_per_step * args.steps,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "iterations_per_scale_mean": iters.sum(axis=2).mean(axis=0).tolist(),
+        "pixel_iterations_per_pair": float(sum(nx * ny * iters[:, s].sum() for s, (nx, ny) in enumerate(sizes)) / npairs),
+        "flow_checksum": checksum,
+    }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--groups", type=int, default=0, help="solver groups (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -92,6 +92,13 @@ RVDD_API int rvdd_tvl1_flow_dev(rvdd_ctx *ctx, const float *gray_dev, int nframe
  * the results are invalid.  Synchronises `stream`. */
 RVDD_API int rvdd_solver_status(rvdd_ctx *ctx, void *stream);
 
+/* Timing of the dominant kernel for the roofline report: with profiling enabled every rvdd_tvl1_flow_dev call
+ * brackets its persistent-solver launch with a pair of CUDA events on the call's stream.  rvdd_profile_read waits
+ * for them, writes the elapsed milliseconds of up to `cap` launches (oldest first), clears the list and returns
+ * how many it wrote (negative on error). */
+RVDD_API int rvdd_profile(rvdd_ctx *ctx, int enable);
+RVDD_API int rvdd_profile_read(rvdd_ctx *ctx, float *solver_ms, int cap);
+
 /* Test hook: copy level `level` of the normalised + presmoothed pyramid (which: 0 = I0, 1 = I1) that the last
  * rvdd_tvl1_flow_dev call built for pair `pair` (tvl1flow_lib.c:380-401) into dst_dev (nx[level]*ny[level]
  * floats), so each pyramid stage can be checked against image_normalization / gaussian / zoom_out. */

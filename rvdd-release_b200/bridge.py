@@ -40,6 +40,8 @@ _SIGNATURES = {
     "rvdd_tvl1_flow_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_int, C.POINTER(TVL1Params), C.c_void_p, C.c_void_p, C.c_void_p]),
     "rvdd_solver_status": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rvdd_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "rvdd_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
     "rvdd_debug_level_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "rvdd_warp_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
                       + [C.c_longlong] * 8 + [C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]),
@@ -150,6 +152,18 @@ class Bridge:
         if check:
             self.check(gray.device)
         return (flow, iters) if trace else flow
+
+    def profile(self, enable=True):
+        """Bracket every solver launch with CUDA events (roofline report of bench.py)."""
+        self._ck(self.lib.rvdd_profile(self.ctx, 1 if enable else 0))
+
+    def profile_read(self, cap=4096):
+        """-> list of solver-kernel durations in ms since the last read."""
+        buf = (C.c_float * cap)()
+        n = self.lib.rvdd_profile_read(self.ctx, buf, cap)
+        if n < 0:
+            raise BridgeError("rvdd_profile_read failed")
+        return [buf[i] for i in range(n)]
 
     def debug_level(self, pair, which, level, nx, ny):
         """Pyramid level of the last tvl1_flow call (test hook, rvdd_debug_level_dev)."""

@@ -164,6 +164,10 @@ struct rvdd_ctx {
     DevBuf e_frames, e_gray, e_flow, e_hw2, e_warp, e_iters;
     cudaStream_t st_compute = nullptr, st_in = nullptr, st_out = nullptr;
     std::vector<cudaEvent_t> events;
+    // optional timing of the solver launches (rvdd_profile / rvdd_profile_read)
+    bool prof = false;
+    std::vector<cudaEvent_t> prof_ev;   // begin/end pairs
+    int prof_n = 0;
 };
 
 extern "C" int rvdd_create(rvdd_ctx **out)
@@ -205,6 +209,7 @@ extern "C" int rvdd_destroy(rvdd_ctx *c)
         if (c->ring_ev[i]) cudaEventDestroy(c->ring_ev[i]);
     }
     for (cudaEvent_t ev : c->events) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : c->prof_ev) cudaEventDestroy(ev);
     if (c->st_compute) cudaStreamDestroy(c->st_compute);
     if (c->st_in) cudaStreamDestroy(c->st_in);
     if (c->st_out) cudaStreamDestroy(c->st_out);
@@ -328,8 +333,42 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
     A.ngroups = G; A.ctas_per_group = C;
     A.spin_limit = 4000000000LL;                             // ~2 s at 2 GHz
     if (iters) CK(cudaMemsetAsync(iters, 0, sizeof(int) * (size_t)K * RVDD_TRACE_SCALES * p.nwarps, st));
+    if (c->prof) {
+        if ((int)c->prof_ev.size() < 2 * (c->prof_n + 1)) {
+            cudaEvent_t a, b;
+            CK(cudaEventCreate(&a));
+            CK(cudaEventCreate(&b));
+            c->prof_ev.push_back(a);
+            c->prof_ev.push_back(b);
+        }
+        CK(cudaEventRecord(c->prof_ev[2 * c->prof_n], st));
+    }
     CK(launch_solver(A, st));
+    if (c->prof) {
+        CK(cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st));
+        c->prof_n++;
+    }
     return 0;
+}
+
+extern "C" int rvdd_profile(rvdd_ctx *c, int enable)
+{
+    if (!c) return fail("rvdd_profile: null context");
+    c->prof = enable != 0;
+    c->prof_n = 0;
+    return 0;
+}
+
+extern "C" int rvdd_profile_read(rvdd_ctx *c, float *solver_ms, int cap)
+{
+    if (!c) return -1;
+    int n = c->prof_n < cap ? c->prof_n : cap;
+    for (int i = 0; i < n; i++) {
+        if (cudaEventSynchronize(c->prof_ev[2 * i + 1]) != cudaSuccess) return -1;
+        if (cudaEventElapsedTime(&solver_ms[i], c->prof_ev[2 * i], c->prof_ev[2 * i + 1]) != cudaSuccess) return -1;
+    }
+    c->prof_n = 0;
+    return n;
 }
 
 extern "C" int rvdd_solver_status(rvdd_ctx *c, void *stream)

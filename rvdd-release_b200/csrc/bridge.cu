@@ -325,6 +325,7 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
     A.taut = p.tau / p.theta;                                // :233
     A.eps2 = p.epsilon * p.epsilon;                          // :163
     A.zoom_mul = (float)1.0 / p.zfactor;                     // :431
+    A.g0f = rvdd_grad_zero_f32();
     A.pyr0 = pyr; A.pyr1 = pyr + (long long)K * P.total; A.pyr_stride = P.total;
     A.flow_out = flow;
     A.scratch = (float *)c->scratch.p; A.scratch_stride = scratch_stride; A.plane = plane;

@@ -26,7 +26,7 @@ struct SolverArgs {
     int nx[RVDD_MAX_SCALES], ny[RVDD_MAX_SCALES];
     long long off[RVDD_MAX_SCALES];
     float zfx[RVDD_MAX_SCALES], zfy[RVDD_MAX_SCALES];   // zoom_in factors towards level s (from s+1), zoom.c:95-96
-    float l_t, theta, taut, eps2, zoom_mul;
+    float l_t, theta, taut, eps2, zoom_mul, g0f;   // g0f: GRAD_IS_ZERO as a float threshold (exact_math.h)
     const float *pyr0, *pyr1;           // [npairs][pyr_stride]
     long long pyr_stride;
     float *flow_out;                    // [npairs][2][nx0*ny0]

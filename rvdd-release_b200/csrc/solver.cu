@@ -84,8 +84,8 @@ __device__ __forceinline__ double group_sum(const GroupCtx &g, int slot, double 
 
 // Distribute the image over the group's warps: column segments of 32*V pixels, strips of `rows` rows.
 template <int V>
-__device__ __forceinline__ double iterate_group(const IterPtrs &P, int nx, int ny, float l_t, float theta, float taut,
-                                                int gwarp, int nwarps_group)
+__device__ __forceinline__ double iterate_group(const IterPtrs &P, int nx, int ny, const IterConsts &K, int gwarp,
+                                                int nwarps_group)
 {
     const int lane = threadIdx.x & 31;
     const StripPlan sp = plan_strips<V>(nx, ny, nwarps_group);
@@ -96,7 +96,7 @@ __device__ __forceinline__ double iterate_group(const IterPtrs &P, int nx, int n
         const int x0 = col * segw + lane * V;
         const int y0 = strip * rows;
         const int y1 = min(ny, y0 + rows);
-        if (x0 < nx) err += iterate_strip<V>(P, x0, y0, y1, nx, ny, l_t, theta, taut);
+        if (x0 < nx) err += iterate_strip<V>(P, x0, col * segw, y0, y1, nx, ny, K);
     }
     return err;
 }
@@ -130,9 +130,12 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 2) solver_kernel(const SolverA
     float *S = A.scratch + (long long)group * A.scratch_stride;
     const long long PL = A.plane;
     float *I1x = S, *I1y = S + PL, *gx = S + 2 * PL, *gy = S + 3 * PL, *g2 = S + 4 * PL, *rc = S + 5 * PL;
-    float *ub[2][2] = {{S + 6 * PL, S + 7 * PL}, {S + 8 * PL, S + 9 * PL}};
-    float *pb[2][4] = {{S + 10 * PL, S + 11 * PL, S + 12 * PL, S + 13 * PL},
-                       {S + 14 * PL, S + 15 * PL, S + 16 * PL, S + 17 * PL}};
+    // flow and dual variable are double-buffered: plane 6 + 2*buf + comp and 10 + 4*buf + comp (no pointer tables:
+    // indexing a local array of pointers would force generic loads and local memory)
+#define UB(buf, comp) (S + (6 + 2 * (buf) + (comp)) * PL)
+#define PB(buf, comp) (S + (10 + 4 * (buf) + (comp)) * PL)
+    IterConsts K;
+    K.l_t = A.l_t; K.theta = A.theta; K.taut = A.taut; K.g0f = A.g0f;
 
     for (int pair = group; pair < A.npairs; pair += A.ngroups) {
         const float *P0 = A.pyr0 + (long long)pair * A.pyr_stride;
@@ -145,21 +148,21 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 2) solver_kernel(const SolverA
 
             if (s == A.S - 1) {
                 // ---- flow = 0 at the coarsest scale (:404-405)
-                for (int i = gtid; i < n; i += gthreads) { ub[uc][0][i] = 0.f; ub[uc][1][i] = 0.f; }
+                for (int i = gtid; i < n; i += gthreads) { UB(uc, 0)[i] = 0.f; UB(uc, 1)[i] = 0.f; }
                 if (s < A.fscale && !group_sync(g, &s_flag)) return;
             }
             if (s >= A.fscale) {
                 // ---- per-scale setup: p = 0 (:134-138), centred gradient of I1 (:131, mask.c:149-206)
                 for (int i = gtid; i < n; i += gthreads) {
                     const int y = i / nx, x = i - y * nx;
-                    pb[pc][0][i] = 0.f; pb[pc][1][i] = 0.f; pb[pc][2][i] = 0.f; pb[pc][3][i] = 0.f;
+                    PB(pc, 0)[i] = 0.f; PB(pc, 1)[i] = 0.f; PB(pc, 2)[i] = 0.f; PB(pc, 3)[i] = 0.f;
                     cgrad_px(I1, x, y, nx, ny, &I1x[i], &I1y[i]);
                 }
                 if (!group_sync(g, &s_flag)) return;
 
                 for (int w = 0; w < A.nwarps; w++) {
                     // ---- warp constants (:143-159): bicubic samples of I1, I1x, I1y at x + u
-                    const float *u1 = ub[uc][0], *u2 = ub[uc][1];
+                    const float *u1 = UB(uc, 0), *u2 = UB(uc, 1);
                     for (int i = gtid; i < n; i += gthreads) {
                         const int y = i / nx, x = i - y * nx;
                         warp_consts_px(I0, I1, I1x, I1y, u1[i], u2[i], x, y, nx, ny, &gx[i], &gy[i], &g2[i], &rc[i]);
@@ -172,14 +175,13 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 2) solver_kernel(const SolverA
                     while (err > A.eps2 && it < RVDD_MAX_ITERATIONS) {
                         it++;
                         IterPtrs P;
-                        P.u1 = ub[uc][0]; P.u2 = ub[uc][1];
-                        P.p11 = pb[pc][0]; P.p12 = pb[pc][1]; P.p21 = pb[pc][2]; P.p22 = pb[pc][3];
-                        P.nu1 = ub[uc ^ 1][0]; P.nu2 = ub[uc ^ 1][1];
-                        P.np11 = pb[pc ^ 1][0]; P.np12 = pb[pc ^ 1][1]; P.np21 = pb[pc ^ 1][2]; P.np22 = pb[pc ^ 1][3];
+                        P.u1 = UB(uc, 0); P.u2 = UB(uc, 1);
+                        P.p11 = PB(pc, 0); P.p12 = PB(pc, 1); P.p21 = PB(pc, 2); P.p22 = PB(pc, 3);
+                        P.nu1 = UB(uc ^ 1, 0); P.nu2 = UB(uc ^ 1, 1);
+                        P.np11 = PB(pc ^ 1, 0); P.np12 = PB(pc ^ 1, 1); P.np21 = PB(pc ^ 1, 2); P.np22 = PB(pc ^ 1, 3);
                         P.gx = gx; P.gy = gy; P.g2 = g2; P.rc = rc;
-                        double e = ((nx & 3) == 0)
-                                       ? iterate_group<4>(P, nx, ny, A.l_t, A.theta, A.taut, gwarp, gwarps)
-                                       : iterate_group<1>(P, nx, ny, A.l_t, A.theta, A.taut, gwarp, gwarps);
+                        double e = ((nx & 3) == 0) ? iterate_group<4>(P, nx, ny, K, gwarp, gwarps)
+                                                   : iterate_group<1>(P, nx, ny, K, gwarp, gwarps);
                         // CTA partial in a fixed order, then the group reduction rides on the barrier
                         for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
                         if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = e;
@@ -207,8 +209,8 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 2) solver_kernel(const SolverA
             if (s > 0) {
                 // ---- zoom_in to the next finer level and rescale (:425-433, zoom.c:85-109)
                 const int fx_n = A.nx[s - 1], fy_n = A.ny[s - 1], fn = fx_n * fy_n;
-                const float *c1 = ub[uc][0], *c2 = ub[uc][1];
-                float *f1 = ub[uc ^ 1][0], *f2 = ub[uc ^ 1][1];
+                const float *c1 = UB(uc, 0), *c2 = UB(uc, 1);
+                float *f1 = UB(uc ^ 1, 0), *f2 = UB(uc ^ 1, 1);
                 const float zx = A.zfx[s - 1], zy = A.zfy[s - 1];
                 for (int i = gtid; i < fn; i += gthreads) {
                     const int y = i / fx_n, x = i - y * fx_n;
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 2) solver_kernel(const SolverA
             } else {
                 // ---- finest flow -> caller's planar (u, v) buffer (:374-375)
                 float *o1 = A.flow_out + (long long)pair * 2 * n, *o2 = o1 + n;
-                const float *c1 = ub[uc][0], *c2 = ub[uc][1];
+                const float *c1 = UB(uc, 0), *c2 = UB(uc, 1);
                 for (int i = gtid; i < n; i += gthreads) { o1[i] = c1[i]; o2[i] = c2[i]; }
             }
             if (!group_sync(g, &s_flag)) return;

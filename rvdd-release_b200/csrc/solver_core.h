@@ -39,6 +39,10 @@ struct IterPtrs {
     const float *gx, *gy, *g2, *rc;                     // per-warp constants
 };
 
+struct IterConsts {
+    float l_t, theta, taut, g0f;
+};
+
 // What one lane carries for one image row: the NEW flow at its V pixels plus the right neighbour, the OLD dual
 // variable, and the residual terms.
 template <int V> struct RowState {
@@ -48,85 +52,155 @@ template <int V> struct RowState {
     float res[V];
 };
 
-// Load row y at columns x0..x0+V (the extra column only if it exists) and run TH + primal update there.
-// up12 / up22: p12 / p22 of row y-1 at the same V+1 columns (ignored when y == 0).
-template <int V>
-RVDD_HD void eval_row(const IterPtrs &P, int x0, int y, int nx, int ny, float l_t, float theta,
-                                         const float (&up12)[V + 1], const float (&up22)[V + 1], RowState<V> &R)
+// Where a lane's pixels sit relative to the image border; fixed for a whole strip.
+struct LaneEdges {
+    bool left;       // x0 == 0: the lane's first pixel is the first column
+    bool right;      // a right neighbour column x0 + V exists
+    bool last_own;   // x0 + V == nx: the lane's last pixel is the last column
+    bool last_nb;    // x0 + V == nx - 1: the right neighbour is the last column (only possible when V == 1)
+    bool edge_warp;  // some lane of this warp touches the first or last column (warp-uniform)
+};
+
+template <int V> RVDD_HD LaneEdges lane_edges(int x0, int nx, int warp_x0)
 {
-    const long long base = (long long)y * nx + x0;
-    const bool right = (x0 + V < nx);
+    LaneEdges e;
+    e.left = (x0 == 0);
+    e.right = (x0 + V < nx);
+    e.last_own = (x0 + V == nx);
+    e.last_nb = (V == 1) && (x0 + V == nx - 1);
+    e.edge_warp = (warp_x0 == 0) || (warp_x0 + 32 * V + 1 >= nx);
+    return e;
+}
+
+// Load row y at columns x0..x0+V (the extra column only if it exists) and run TH + primal update there.
+// `row` points at (y, x0) as an element offset; up12 / up22 hold p12 / p22 of row y-1 at the same V+1 columns
+// (zeros when y == 0).  first/last: y == 0 / y == ny-1.
+template <int V>
+RVDD_HD void eval_row(const IterPtrs &P, long long row, const LaneEdges &E, bool first, bool last, const IterConsts &K,
+                      const float (&up12)[V + 1], const float (&up22)[V + 1], RowState<V> &R)
+{
     float u1[V + 1], u2[V + 1], gx[V + 1], gy[V + 1], g2[V + 1], rc[V + 1], a11[V + 1], a21[V + 1];
     {
         float t[V];
-        Vec<V>::ld(P.u1 + base, t);
+        Vec<V>::ld(P.u1 + row, t);
 #pragma unroll
         for (int j = 0; j < V; j++) u1[j] = t[j];
-        Vec<V>::ld(P.u2 + base, t);
+        Vec<V>::ld(P.u2 + row, t);
 #pragma unroll
         for (int j = 0; j < V; j++) u2[j] = t[j];
-        Vec<V>::ld(P.gx + base, t);
+        Vec<V>::ld(P.gx + row, t);
 #pragma unroll
         for (int j = 0; j < V; j++) gx[j] = t[j];
-        Vec<V>::ld(P.gy + base, t);
+        Vec<V>::ld(P.gy + row, t);
 #pragma unroll
         for (int j = 0; j < V; j++) gy[j] = t[j];
-        Vec<V>::ld(P.g2 + base, t);
+        Vec<V>::ld(P.g2 + row, t);
 #pragma unroll
         for (int j = 0; j < V; j++) g2[j] = t[j];
-        Vec<V>::ld(P.rc + base, t);
+        Vec<V>::ld(P.rc + row, t);
 #pragma unroll
         for (int j = 0; j < V; j++) rc[j] = t[j];
-        Vec<V>::ld(P.p11 + base, t);
+        Vec<V>::ld(P.p11 + row, t);
 #pragma unroll
         for (int j = 0; j < V; j++) a11[j] = t[j];
-        Vec<V>::ld(P.p21 + base, t);
+        Vec<V>::ld(P.p21 + row, t);
 #pragma unroll
         for (int j = 0; j < V; j++) a21[j] = t[j];
-        Vec<V>::ld(P.p12 + base, t);
+        Vec<V>::ld(P.p12 + row, t);
 #pragma unroll
         for (int j = 0; j < V; j++) R.p12[j] = t[j];
-        Vec<V>::ld(P.p22 + base, t);
+        Vec<V>::ld(P.p22 + row, t);
 #pragma unroll
         for (int j = 0; j < V; j++) R.p22[j] = t[j];
     }
     u1[V] = u2[V] = gx[V] = gy[V] = g2[V] = rc[V] = a11[V] = a21[V] = 0.f;
     R.p12[V] = R.p22[V] = 0.f;
-    if (right) {
-        const long long q = base + V;
+    if (E.right) {
+        const long long q = row + V;
         u1[V] = P.u1[q]; u2[V] = P.u2[q]; gx[V] = P.gx[q]; gy[V] = P.gy[q]; g2[V] = P.g2[q]; rc[V] = P.rc[q];
         a11[V] = P.p11[q]; a21[V] = P.p21[q]; R.p12[V] = P.p12[q]; R.p22[V] = P.p22[q];
     }
     float l11 = 0.f, l21 = 0.f;
-    if (x0 > 0) { l11 = P.p11[base - 1]; l21 = P.p21[base - 1]; }
-#pragma unroll
-    for (int j = 0; j <= V; j++) {
-        if (j == V && !right) break;
-        const int x = x0 + j;
-        const float d1 = rvdd_div_px(a11[j], j ? a11[j - 1] : l11, R.p12[j], up12[j], x, y, nx, ny);
-        const float d2 = rvdd_div_px(a21[j], j ? a21[j - 1] : l21, R.p22[j], up22[j], x, y, nx, ny);
-        rvdd_primal_px(u1[j], u2[j], gx[j], gy[j], g2[j], rc[j], d1, d2, l_t, theta, &R.n1[j], &R.n2[j]);
-    }
-    if (!right) { R.n1[V] = 0.f; R.n2[V] = 0.f; }
+    if (!E.left) { l11 = P.p11[row - 1]; l21 = P.p21[row - 1]; }
 #pragma unroll
     for (int j = 0; j < V; j++) {
         R.p11[j] = a11[j];
         R.p21[j] = a21[j];
-        R.res[j] = rvdd_residual_px(R.n1[j], u1[j], R.n2[j], u2[j]);
     }
+    // divergence of p: operands zeroed where the stencil leaves the image, see rvdd_div_inner
+    float d1[V + 1], d2[V + 1];
+#pragma unroll
+    for (int j = 0; j <= V; j++) {
+        const bool lastcol = (j == V - 1) ? E.last_own : ((j == V) ? E.last_nb : false);
+        const float a1 = lastcol ? 0.f : a11[j], a2 = lastcol ? 0.f : a21[j];
+        const float b1 = last ? 0.f : R.p12[j], b2 = last ? 0.f : R.p22[j];
+        d1[j] = rvdd_div_inner(a1, j ? a11[j - 1] : l11, b1, up12[j]);
+        d2[j] = rvdd_div_inner(a2, j ? a21[j - 1] : l21, b2, up22[j]);
+    }
+    if (E.edge_warp && !first && !last) {
+        // first / last column of a middle row: the reference associates (s + b) - bu (mask.c:80-81)
+        if (E.left) {
+            d1[0] = rvdd_div_edge(a11[0], R.p12[0], up12[0]);
+            d2[0] = rvdd_div_edge(a21[0], R.p22[0], up22[0]);
+        }
+        if (E.last_own) {
+            d1[V - 1] = rvdd_div_edge(-(V > 1 ? a11[V > 1 ? V - 2 : 0] : l11), R.p12[V - 1], up12[V - 1]);
+            d2[V - 1] = rvdd_div_edge(-(V > 1 ? a21[V > 1 ? V - 2 : 0] : l21), R.p22[V - 1], up22[V - 1]);
+        }
+        if (E.last_nb) {
+            d1[V] = rvdd_div_edge(-a11[V - 1], R.p12[V], up12[V]);
+            d2[V] = rvdd_div_edge(-a21[V - 1], R.p22[V], up22[V]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j <= V; j++)
+        rvdd_primal_px(u1[j], u2[j], gx[j], gy[j], g2[j], rc[j], d1[j], d2[j], K.l_t, K.theta, K.g0f, &R.n1[j], &R.n2[j]);
+#pragma unroll
+    for (int j = 0; j < V; j++) R.res[j] = rvdd_residual_px(R.n1[j], u1[j], R.n2[j], u2[j]);
 }
 
-// One lane's strip: columns x0..x0+V-1, rows y0..y1-1.  Returns the residual sum of those pixels.
+// Dual update of row `cur` (its forward differences need the new flow of the row below, `nxt`), stores of the new
+// flow and dual variable, residual accumulation.
 template <int V>
-RVDD_HD double iterate_strip(const IterPtrs &P, int x0, int y0, int y1, int nx, int ny, float l_t,
-                                                float theta, float taut)
+RVDD_HD void finish_row(const IterPtrs &P, long long row, const LaneEdges &E, bool down, const IterConsts &K,
+                        const RowState<V> &cur, const RowState<V> &nxt, double &err)
+{
+    float o11[V], o12[V], o21[V], o22[V], o1[V], o2[V];
+#pragma unroll
+    for (int j = 0; j < V; j++) {
+        // forward differences of the NEW flow (mask.c:98-141): zero on the last column / row
+        const bool lastcol = (j == V - 1) && E.last_own;
+        const float u1x = lastcol ? 0.f : FSUB(cur.n1[j + 1], cur.n1[j]);
+        const float u2x = lastcol ? 0.f : FSUB(cur.n2[j + 1], cur.n2[j]);
+        const float u1y = down ? FSUB(nxt.n1[j], cur.n1[j]) : 0.f;
+        const float u2y = down ? FSUB(nxt.n2[j], cur.n2[j]) : 0.f;
+        o11[j] = cur.p11[j]; o12[j] = cur.p12[j]; o21[j] = cur.p21[j]; o22[j] = cur.p22[j];
+        rvdd_dual_px(&o11[j], &o12[j], u1x, u1y, K.taut);
+        rvdd_dual_px(&o21[j], &o22[j], u2x, u2y, K.taut);
+        o1[j] = cur.n1[j]; o2[j] = cur.n2[j];
+        err += (double)cur.res[j];
+    }
+    Vec<V>::st(P.nu1 + row, o1);
+    Vec<V>::st(P.nu2 + row, o2);
+    Vec<V>::st(P.np11 + row, o11);
+    Vec<V>::st(P.np12 + row, o12);
+    Vec<V>::st(P.np21 + row, o21);
+    Vec<V>::st(P.np22 + row, o22);
+}
+
+// One lane's strip: columns x0..x0+V-1, rows y0..y1-1.  Returns the residual sum of those pixels.  The row loop is
+// unrolled by two so the "current" and "next" row states swap roles without being copied.
+template <int V>
+RVDD_HD double iterate_strip(const IterPtrs &P, int x0, int warp_x0, int y0, int y1, int nx, int ny, const IterConsts &K)
 {
     double err = 0.0;
+    const LaneEdges E = lane_edges<V>(x0, nx, warp_x0);
     float up12[V + 1], up22[V + 1];
 #pragma unroll
     for (int j = 0; j <= V; j++) up12[j] = up22[j] = 0.f;
+    long long row = (long long)y0 * nx + x0;
     if (y0 > 0) {
-        const long long b = (long long)(y0 - 1) * nx + x0;
+        const long long b = row - nx;
         float t[V];
         Vec<V>::ld(P.p12 + b, t);
 #pragma unroll
@@ -134,40 +208,25 @@ RVDD_HD double iterate_strip(const IterPtrs &P, int x0, int y0, int y1, int nx, 
         Vec<V>::ld(P.p22 + b, t);
 #pragma unroll
         for (int j = 0; j < V; j++) up22[j] = t[j];
-        if (x0 + V < nx) { up12[V] = P.p12[b + V]; up22[V] = P.p22[b + V]; }
+        if (E.right) { up12[V] = P.p12[b + V]; up22[V] = P.p22[b + V]; }
     }
-    RowState<V> cur, nxt;
-    eval_row<V>(P, x0, y0, nx, ny, l_t, theta, up12, up22, cur);
-    for (int y = y0; y < y1; y++) {
-        const bool down = (y + 1 < ny);
-        if (down) eval_row<V>(P, x0, y + 1, nx, ny, l_t, theta, cur.p12, cur.p22, nxt);
-        float o11[V], o12[V], o21[V], o22[V], o1[V], o2[V];
-#pragma unroll
-        for (int j = 0; j < V; j++) {
-            const int x = x0 + j;
-            // forward differences of the NEW flow (mask.c:98-141): zero on the last column / row
-            const float u1x = (x < nx - 1) ? FSUB(cur.n1[j + 1], cur.n1[j]) : 0.f;
-            const float u2x = (x < nx - 1) ? FSUB(cur.n2[j + 1], cur.n2[j]) : 0.f;
-            const float u1y = down ? FSUB(nxt.n1[j], cur.n1[j]) : 0.f;
-            const float u2y = down ? FSUB(nxt.n2[j], cur.n2[j]) : 0.f;
-            o11[j] = cur.p11[j]; o12[j] = cur.p12[j]; o21[j] = cur.p21[j]; o22[j] = cur.p22[j];
-            rvdd_dual_px(&o11[j], &o12[j], u1x, u1y, taut);
-            rvdd_dual_px(&o21[j], &o22[j], u2x, u2y, taut);
-            o1[j] = cur.n1[j]; o2[j] = cur.n2[j];
-            err += (double)cur.res[j];
-        }
-        const long long base = (long long)y * nx + x0;
-        Vec<V>::st(P.nu1 + base, o1);
-        Vec<V>::st(P.nu2 + base, o2);
-        Vec<V>::st(P.np11 + base, o11);
-        Vec<V>::st(P.np12 + base, o12);
-        Vec<V>::st(P.np21 + base, o21);
-        Vec<V>::st(P.np22 + base, o22);
-        if (down) cur = nxt;
+    RowState<V> A, B;
+    eval_row<V>(P, row, E, y0 == 0, y0 == ny - 1, K, up12, up22, A);
+    int y = y0;
+    while (true) {
+        bool down = (y + 1 < ny);
+        if (down) eval_row<V>(P, row + nx, E, false, y + 2 == ny, K, A.p12, A.p22, B);
+        finish_row<V>(P, row, E, down, K, A, B, err);
+        row += nx;
+        if (++y >= y1) break;
+        down = (y + 1 < ny);
+        if (down) eval_row<V>(P, row + nx, E, false, y + 2 == ny, K, B.p12, B.p22, A);
+        finish_row<V>(P, row, E, down, K, B, A, err);
+        row += nx;
+        if (++y >= y1) break;
     }
     return err;
 }
-
 
 // ------------------------------------------------------------------------------------------------ per-pixel phases
 

@@ -63,7 +63,7 @@ extern "C" void hs_resample(const float *src, int nx, int ny, float *dst, int nx
 }
 
 template <int V>
-static double iterate_image(const IterPtrs &P, int nx, int ny, float l_t, float theta, float taut, int nwarps)
+static double iterate_image(const IterPtrs &P, int nx, int ny, const IterConsts &K, int nwarps)
 {
     const StripPlan sp = plan_strips<V>(nx, ny, nwarps);
     double err = 0.0;
@@ -72,7 +72,7 @@ static double iterate_image(const IterPtrs &P, int nx, int ny, float l_t, float 
         const int y0 = strip * sp.rows, y1 = (y0 + sp.rows < ny) ? y0 + sp.rows : ny;
         for (int lane = 0; lane < 32; lane++) {
             const int x0 = col * 32 * V + lane * V;
-            if (x0 < nx) err += iterate_strip<V>(P, x0, y0, y1, nx, ny, l_t, theta, taut);
+            if (x0 < nx) err += iterate_strip<V>(P, x0, col * 32 * V, y0, y1, nx, ny, K);
         }
     }
     return err;
@@ -146,8 +146,10 @@ extern "C" int hs_tvl1flow(const float *I0, const float *I1, float *u, int nx0, 
                 P.nu1 = ub[uc ^ 1][0]; P.nu2 = ub[uc ^ 1][1];
                 P.np11 = pb[pc ^ 1][0]; P.np12 = pb[pc ^ 1][1]; P.np21 = pb[pc ^ 1][2]; P.np22 = pb[pc ^ 1][3];
                 P.gx = gx; P.gy = gy; P.g2 = g2; P.rc = rc;
-                const double tot = ((w_ & 3) == 0 && !force_scalar) ? iterate_image<4>(P, w_, h_, l_t, theta, taut, nwarps_group)
-                                                                    : iterate_image<1>(P, w_, h_, l_t, theta, taut, nwarps_group);
+                IterConsts K;
+                K.l_t = l_t; K.theta = theta; K.taut = taut; K.g0f = rvdd_grad_zero_f32();
+                const double tot = ((w_ & 3) == 0 && !force_scalar) ? iterate_image<4>(P, w_, h_, K, nwarps_group)
+                                                                    : iterate_image<1>(P, w_, h_, K, nwarps_group);
                 err = FDIV((float)tot, (float)n);
                 uc ^= 1; pc ^= 1;
             }

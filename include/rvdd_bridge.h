@@ -99,6 +99,12 @@ RVDD_API int rvdd_solver_status(rvdd_ctx *ctx, void *stream);
 RVDD_API int rvdd_profile(rvdd_ctx *ctx, int enable);
 RVDD_API int rvdd_profile_read(rvdd_ctx *ctx, float *solver_ms, int cap);
 
+/* Test hook: run `blocks` x 256 threads x `iters` pseudo-random trials of the kernels' straight-line exact
+ * division / hypot fast paths against IEEE division and the double-precision square root on the device.
+ * counters_host[6] = {hypot trials, hypot fallbacks, hypot MISMATCHES, div trials, div rejected, div MISMATCHES};
+ * the two mismatch counts must be zero. */
+RVDD_API int rvdd_selftest_fastmath(unsigned long long seed, int blocks, int iters, unsigned long long *counters_host);
+
 /* Test hook: copy level `level` of the normalised + presmoothed pyramid (which: 0 = I0, 1 = I1) that the last
  * rvdd_tvl1_flow_dev call built for pair `pair` (tvl1flow_lib.c:380-401) into dst_dev (nx[level]*ny[level]
  * floats), so each pyramid stage can be checked against image_normalization / gaussian / zoom_out. */

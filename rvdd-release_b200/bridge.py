@@ -42,6 +42,7 @@ _SIGNATURES = {
     "rvdd_solver_status": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rvdd_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "rvdd_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
+    "rvdd_selftest_fastmath": (C.c_int, [C.c_ulonglong, C.c_int, C.c_int, C.POINTER(C.c_ulonglong)]),
     "rvdd_debug_level_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "rvdd_warp_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
                       + [C.c_longlong] * 8 + [C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]),
@@ -55,7 +56,7 @@ EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 def load_library(path=None):
     """dlopen libBridge.so and declare every prototype.  Raises if the library has not been built."""
-    path = path or DEFAULT_LIB
+    path = path or os.environ.get("RVDD_BRIDGE_LIB") or DEFAULT_LIB
     if not os.path.exists(path):
         raise BridgeError("%s not found: build it with `python rvdd-release_b200/build.py` "
                           "(there is no CPU fallback)" % path)

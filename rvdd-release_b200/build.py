@@ -14,7 +14,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-SOURCES = ["bridge.cu", "prep.cu", "solver.cu", "warp.cu"]
+SOURCES = ["bridge.cu", "prep.cu", "solver.cu", "warp.cu", "selftest.cu"]
 LIB = os.path.join(PKG, "lib", "libBridge.so")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
@@ -35,27 +35,39 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_lib(force=False, verbose=False):
-    """Compile csrc/*.cu -> lib/libBridge.so (sm_100a).  Returns the library path."""
+def build_lib(force=False, verbose=False, variant=None, defines=()):
+    """Compile csrc/*.cu -> lib/libBridge.so (sm_100a).  Returns the library path.
+
+    variant/defines build an experimental lib/libBridge_<variant>.so with extra -D macros (tuning runs only; select
+    it at run time with RVDD_BRIDGE_LIB)."""
+    if variant:
+        return _build(os.path.join(PKG, "lib", "libBridge_%s.so" % variant), os.path.join(PKG, "lib", "obj_" + variant),
+                      verbose, ["-D" + d for d in defines], install=False)
     if not force and not needs_build():
         return LIB
+    return _build(LIB, os.path.join(PKG, "lib", "obj"), verbose, [], install=True)
+
+
+def _build(LIB, objdir, verbose, extra, install):
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    objdir = os.path.join(PKG, "lib", "obj")
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     objs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         subprocess.run(cmd, check=True)
         objs.append(obj)
     tmp = LIB + ".tmp"
     subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs, check=True)
     os.replace(tmp, LIB)
-    os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
-    shutil.copy2(LIB, os.path.join(ROOT, "build", "libBridge.so"))
+    if install:
+        os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
+        shutil.copy2(LIB, os.path.join(ROOT, "build", "libBridge.so"))
     return LIB
 
 
 if __name__ == "__main__":
-    print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    _variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    _defs = [a[2:] for a in sys.argv if a.startswith("-D")]
+    print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=_variant, defines=_defs))

@@ -19,7 +19,16 @@
 
 namespace rvdd {
 
-#define SOLVER_THREADS 256
+// 192 threads x 2 CTAs per SM = 12 warps with up to 168 registers each: the 4-pixel lane state (two row states, the
+// staged inputs, the address arithmetic) spills at 128 registers, and spill reloads sit on the critical path of every
+// row.  Measured on B200 (29 pairs, 1280x720): 256x2 (128 regs) 58 ms, 256x1 (207 regs) 52 ms, 384x1 / 192x2
+// (168 regs) 46 ms.
+#ifndef SOLVER_THREADS
+#define SOLVER_THREADS 192
+#endif
+#ifndef SOLVER_MIN_CTAS
+#define SOLVER_MIN_CTAS 2
+#endif
 #define SOLVER_WARPS (SOLVER_THREADS / 32)
 
 int solver_threads() { return SOLVER_THREADS; }
@@ -46,6 +55,7 @@ struct GroupCtx {
 // Returns false if the watchdog fired (somebody waited longer than spin_limit): the kernel then unwinds.
 __device__ __forceinline__ bool group_sync(GroupCtx &g, int *s_flag)
 {
+    asm volatile("fence.proxy.async;" ::: "memory");   // this thread's stores may next be read by bulk async copies
     __syncthreads();
     if (threadIdx.x == 0) {
         g.target += (unsigned)g.nctas;
@@ -82,10 +92,186 @@ __device__ __forceinline__ double group_sum(const GroupCtx &g, int slot, double 
     return *s_val;
 }
 
-// Distribute the image over the group's warps: column segments of 32*V pixels, strips of `rows` rows.
+// ------------------------------------------------------------------------------------------------ strip iteration
+
+#ifndef SOLVER_V
+#define SOLVER_V 4
+#endif
+
+// ---- bulk-copy (TMA) row staging, used when the image width is a multiple of 4 ---------------------------------
+//
+// By Little's law the direct-load strip loop cannot keep HBM busy: a warp asks for one row (5 KB), waits ~2 us for
+// it, computes, and only then asks for the next; with 16 warps per SM (the state of a 4-pixel lane needs ~128
+// registers) that is ~30 KB in flight per SM, good for ~2.5 TB/s.  So every warp stages the rows it is about to
+// process in shared memory with 1-D bulk asynchronous copies (cp.async.bulk global -> shared, completion on an
+// mbarrier): 10 arrays x (128 pixels + a 4-pixel block on either side) per row, two rows per warp in flight.  The
+// copy of row y+3 is issued as soon as row y+1 has been consumed, so the loads of the next rows overlap the
+// arithmetic of the current one.  The right/left neighbour pixels come out of the same staged row.
+
+#define ST_PAD 4                         // pixels staged on either side of the warp's 128
+#define ST_SLOT (128 + 2 * ST_PAD)       // floats per array per row (544 B, a multiple of 16 B)
+#define ST_ROW (10 * ST_SLOT)            // floats per staged row
+#ifndef ST_STAGES
+#define ST_STAGES 2
+#endif
+#define ST_WARP_BYTES (ST_STAGES * ST_ROW * 4 + 64)   // + the mbarriers
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+struct TmaRing {
+    float *stage[ST_STAGES];
+    unsigned long long *bar[ST_STAGES];
+    unsigned uses[ST_STAGES];            // completed uses of each stage (phase parity = uses & 1)
+};
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// One lane of a converged warp.  Unlike `lane == 0`, elect.sync tells the compiler that exactly one thread runs the
+// guarded region, so the bulk copies (uniform-datapath instructions) are issued once instead of in a per-lane loop.
+__device__ __forceinline__ bool elect_one()
+{
+    unsigned pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// elected lane: queue the bulk copies of image row `rowoff` (= y * nx + warp_x0) into `stage`
+__device__ __forceinline__ void tma_issue_row(const IterPtrs &P, long long rowoff, int warp_x0, int nx, float *stage,
+                                              unsigned long long *bar)
+{
+    const int main_px = min(128, nx - warp_x0);
+    const bool right = (warp_x0 + 128 < nx), left = (warp_x0 > 0);
+    const unsigned b_plain = 4u * (unsigned)(main_px + (right ? ST_PAD : 0));
+    const unsigned b_left = b_plain + (left ? 4u * ST_PAD : 0u);
+    mbar_expect_tx(bar, 8u * b_plain + 2u * b_left);
+    float *d = stage + ST_PAD;
+    bulk_g2s(d + 0 * ST_SLOT, P.u1() + rowoff, b_plain, bar);
+    bulk_g2s(d + 1 * ST_SLOT, P.u2() + rowoff, b_plain, bar);
+    bulk_g2s(d + 2 * ST_SLOT, P.gx() + rowoff, b_plain, bar);
+    bulk_g2s(d + 3 * ST_SLOT, P.gy() + rowoff, b_plain, bar);
+    bulk_g2s(d + 4 * ST_SLOT, P.g2() + rowoff, b_plain, bar);
+    bulk_g2s(d + 5 * ST_SLOT, P.rc() + rowoff, b_plain, bar);
+    bulk_g2s(d + 6 * ST_SLOT, P.p12() + rowoff, b_plain, bar);
+    bulk_g2s(d + 7 * ST_SLOT, P.p22() + rowoff, b_plain, bar);
+    const int lo = left ? ST_PAD : 0;    // p11 / p21 also need the pixel to the left of the warp's first
+    bulk_g2s(d + 8 * ST_SLOT - lo, P.p11() + rowoff - lo, b_left, bar);
+    bulk_g2s(d + 9 * ST_SLOT - lo, P.p21() + rowoff - lo, b_left, bar);
+}
+
+// all lanes: wait for stage `st`, then pull this lane's pixels (+ neighbours) out of shared memory
+template <int st>
+__device__ __forceinline__ void tma_take_row(TmaRing &T, int lane, const LaneEdges &E, RowIn<4> &I, int *status)
+{
+    const unsigned parity = T.uses[st] & 1u;
+    bool ok = mbar_try_wait(T.bar[st], parity);
+    for (unsigned spins = 0; !ok; ++spins) {
+        ok = mbar_try_wait(T.bar[st], parity);
+        if (!ok && spins > (1u << 22)) {            // ~ seconds: something is badly wrong, do not hang the GPU
+            atomicExch(status, 2);
+            break;
+        }
+    }
+    T.uses[st]++;
+    const float *s = T.stage[st] + ST_PAD + 4 * lane;
+    float4 v;
+#define TAKE(k, dst)                                                \
+    v = *reinterpret_cast<const float4 *>(s + (k) * ST_SLOT);       \
+    I.dst[0] = v.x; I.dst[1] = v.y; I.dst[2] = v.z; I.dst[3] = v.w; \
+    I.dst[4] = E.right ? s[(k) * ST_SLOT + 4] : 0.f;
+    TAKE(0, u1) TAKE(1, u2) TAKE(2, gx) TAKE(3, gy) TAKE(4, g2) TAKE(5, rc) TAKE(6, p12) TAKE(7, p22) TAKE(8, a11) TAKE(9, a21)
+#undef TAKE
+    I.l11 = E.left ? 0.f : s[8 * ST_SLOT - 1];
+    I.l21 = E.left ? 0.f : s[9 * ST_SLOT - 1];
+}
+
+// One warp's strip with staged rows (V = 4): same arithmetic as iterate_strip<4>, different data path.
+__device__ __forceinline__ double iterate_strip_tma(const IterPtrs &P, TmaRing &T, int lane, int warp_x0, int y0, int y1,
+                                                    int nx, int ny, const IterConsts &K, int *status)
+{
+    const int x0 = warp_x0 + 4 * lane;
+    const bool active = x0 < nx;
+    const LaneEdges E = lane_edges<4>(active ? x0 : 0x3fffff00, nx, warp_x0);
+    const int yend = (y1 < ny) ? y1 : ny - 1;            // last row to evaluate (the strip's halo row if any)
+    const int nr = yend - y0 + 1;
+    const long long wrow = (long long)y0 * nx + warp_x0;
+    double err = 0.0;
+
+    __syncwarp();
+    if (elect_one()) {
+        fence_proxy_async();                             // other CTAs' stores (generic proxy) -> our bulk reads
+        tma_issue_row(P, wrow, warp_x0, nx, T.stage[0], T.bar[0]);
+        if (nr > 1) tma_issue_row(P, wrow + nx, warp_x0, nx, T.stage[1], T.bar[1]);
+    }
+    float up12[5], up22[5];
+    long long row = (long long)y0 * nx + x0;
+    if (active) {
+        load_up_row<4>(P, row, nx, y0, E, up12, up22);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 5; j++) up12[j] = up22[j] = 0.f;
+    }
+
+    RowState<4> A, B;
+    RowIn<4> I;
+    tma_take_row<0>(T, lane, E, I, status);
+    eval_loaded<4>(I, E, y0 == 0, y0 == ny - 1, K, up12, up22, A);
+    __syncwarp();
+    if (nr > 2 && elect_one()) tma_issue_row(P, wrow + 2LL * nx, warp_x0, nx, T.stage[0], T.bar[0]);
+
+    int y = y0, i = 0;                                   // i = y - y0
+    while (true) {
+        bool down = (i + 1 < nr);
+        if (down) {                                      // i is even here: row i+1 sits in stage 1
+            tma_take_row<1>(T, lane, E, I, status);
+            eval_loaded<4>(I, E, false, y + 2 == ny, K, A.p12, A.p22, B);
+            __syncwarp();
+            if (i + 3 < nr && elect_one()) tma_issue_row(P, wrow + (long long)(i + 3) * nx, warp_x0, nx, T.stage[1], T.bar[1]);
+        }
+        finish_row<4>(P, row, E, down, K, A, B, err, active);
+        row += nx; ++i;
+        if (++y >= y1) break;
+        down = (i + 1 < nr);
+        if (down) {                                      // i is odd here: row i+1 sits in stage 0
+            tma_take_row<0>(T, lane, E, I, status);
+            eval_loaded<4>(I, E, false, y + 2 == ny, K, B.p12, B.p22, A);
+            __syncwarp();
+            if (i + 3 < nr && elect_one()) tma_issue_row(P, wrow + (long long)(i + 3) * nx, warp_x0, nx, T.stage[0], T.bar[0]);
+        }
+        finish_row<4>(P, row, E, down, K, B, A, err, active);
+        row += nx; ++i;
+        if (++y >= y1) break;
+    }
+    return err;
+}
+
+// Distribute the image over the group's warps: column segments of 32*V pixels, strips of `rows` rows
+// (iterate_strip, the direct-load version, is in solver_core.h and shared with the host-compiled unit tests).
 template <int V>
-__device__ __forceinline__ double iterate_group(const IterPtrs &P, int nx, int ny, const IterConsts &K, int gwarp,
-                                                int nwarps_group)
+__device__ __forceinline__ double iterate_group(const IterPtrs &P, TmaRing &T, int nx, int ny, const IterConsts &K,
+                                                int gwarp, int nwarps_group, int *status)
 {
     const int lane = threadIdx.x & 31;
     const StripPlan sp = plan_strips<V>(nx, ny, nwarps_group);
@@ -96,19 +282,38 @@ __device__ __forceinline__ double iterate_group(const IterPtrs &P, int nx, int n
         const int x0 = col * segw + lane * V;
         const int y0 = strip * rows;
         const int y1 = min(ny, y0 + rows);
-        if (x0 < nx) err += iterate_strip<V>(P, x0, col * segw, y0, y1, nx, ny, K);
+        if (V == 4) {
+            err += iterate_strip_tma(P, T, lane, col * segw, y0, y1, nx, ny, K, status);
+        } else {
+            if (x0 < nx) err += iterate_strip<V>(P, x0, col * segw, y0, y1, nx, ny, K);
+        }
     }
     return err;
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
 
-__global__ void __launch_bounds__(SOLVER_THREADS, 2) solver_kernel(const SolverArgs A)
+__global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel(const SolverArgs A)
 {
     __shared__ double s_red[SOLVER_WARPS];
     __shared__ double s_val;
     __shared__ int s_flag;
+    extern __shared__ __align__(128) unsigned char s_dyn[];
 
+    // per-warp staging ring for the bulk-copy row pipeline
+    TmaRing T;
+    {
+        unsigned char *base = s_dyn + (size_t)(threadIdx.x >> 5) * ST_WARP_BYTES;
+#pragma unroll
+        for (int k = 0; k < ST_STAGES; k++) {
+            T.stage[k] = reinterpret_cast<float *>(base + (size_t)k * ST_ROW * 4);
+            T.bar[k] = reinterpret_cast<unsigned long long *>(base + (size_t)ST_STAGES * ST_ROW * 4 + 16 * k);
+            T.uses[k] = 0u;
+            if ((threadIdx.x & 31) == 0) mbar_init(T.bar[k], 1u);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+    }
     const int group = blockIdx.x / A.ctas_per_group;
     GroupCtx g;
     g.nctas = A.ctas_per_group;
@@ -175,13 +380,9 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 2) solver_kernel(const SolverA
                     while (err > A.eps2 && it < RVDD_MAX_ITERATIONS) {
                         it++;
                         IterPtrs P;
-                        P.u1 = UB(uc, 0); P.u2 = UB(uc, 1);
-                        P.p11 = PB(pc, 0); P.p12 = PB(pc, 1); P.p21 = PB(pc, 2); P.p22 = PB(pc, 3);
-                        P.nu1 = UB(uc ^ 1, 0); P.nu2 = UB(uc ^ 1, 1);
-                        P.np11 = PB(pc ^ 1, 0); P.np12 = PB(pc ^ 1, 1); P.np21 = PB(pc ^ 1, 2); P.np22 = PB(pc ^ 1, 3);
-                        P.gx = gx; P.gy = gy; P.g2 = g2; P.rc = rc;
-                        double e = ((nx & 3) == 0) ? iterate_group<4>(P, nx, ny, K, gwarp, gwarps)
-                                                   : iterate_group<1>(P, nx, ny, K, gwarp, gwarps);
+                        P.S = S; P.PL = PL; P.uc = uc; P.pc = pc;
+                        double e = ((nx & 3) == 0) ? iterate_group<4>(P, T, nx, ny, K, gwarp, gwarps, A.status)
+                                                   : iterate_group<1>(P, T, nx, ny, K, gwarp, gwarps, A.status);
                         // CTA partial in a fixed order, then the group reduction rides on the barrier
                         for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
                         if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = e;
@@ -236,14 +437,17 @@ cudaError_t solver_max_ctas(int *ctas_per_sm, int *sms)
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, solver_kernel, SOLVER_THREADS, 0);
+    e = cudaFuncSetAttribute(solver_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVER_WARPS * ST_WARP_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, solver_kernel, SOLVER_THREADS,
+                                                         SOLVER_WARPS * ST_WARP_BYTES);
 }
 
 cudaError_t launch_solver(const SolverArgs &args, cudaStream_t st)
 {
     void *params[] = {(void *)&args};
     const dim3 grid(args.ngroups * args.ctas_per_group), block(SOLVER_THREADS);
-    return cudaLaunchCooperativeKernel((const void *)solver_kernel, grid, block, params, 0, st);
+    return cudaLaunchCooperativeKernel((const void *)solver_kernel, grid, block, params, SOLVER_WARPS * ST_WARP_BYTES, st);
 }
 
 }  // namespace rvdd

@@ -33,10 +33,29 @@ template <> struct Vec<1> {
     RVDD_HDM void st(float *p, const float (&v)[1]) { *p = v[0]; }
 };
 
+// All arrays of one iteration are planes of the group's scratch block: plane 2..5 = the per-warp constants, plane
+// 6 + 2*buf + c = flow component c of buffer buf, plane 10 + 4*buf + c = dual variable.  Buffer (uc, pc) is read,
+// the other one written.  Addresses are formed on demand from (S, PL) instead of keeping 16 pointers in registers.
 struct IterPtrs {
-    const float *u1, *u2, *p11, *p12, *p21, *p22;       // read buffers
-    float *nu1, *nu2, *np11, *np12, *np21, *np22;       // write buffers
-    const float *gx, *gy, *g2, *rc;                     // per-warp constants
+    float *S;
+    long long PL;
+    int uc, pc;
+    RVDD_HDX const float *gx() const { return S + 2 * PL; }
+    RVDD_HDX const float *gy() const { return S + 3 * PL; }
+    RVDD_HDX const float *g2() const { return S + 4 * PL; }
+    RVDD_HDX const float *rc() const { return S + 5 * PL; }
+    RVDD_HDX const float *u1() const { return S + (6 + 2 * uc) * PL; }
+    RVDD_HDX const float *u2() const { return S + (7 + 2 * uc) * PL; }
+    RVDD_HDX const float *p11() const { return S + (10 + 4 * pc) * PL; }
+    RVDD_HDX const float *p12() const { return S + (11 + 4 * pc) * PL; }
+    RVDD_HDX const float *p21() const { return S + (12 + 4 * pc) * PL; }
+    RVDD_HDX const float *p22() const { return S + (13 + 4 * pc) * PL; }
+    RVDD_HDX float *nu1() const { return S + (6 + 2 * (uc ^ 1)) * PL; }
+    RVDD_HDX float *nu2() const { return S + (7 + 2 * (uc ^ 1)) * PL; }
+    RVDD_HDX float *np11() const { return S + (10 + 4 * (pc ^ 1)) * PL; }
+    RVDD_HDX float *np12() const { return S + (11 + 4 * (pc ^ 1)) * PL; }
+    RVDD_HDX float *np21() const { return S + (12 + 4 * (pc ^ 1)) * PL; }
+    RVDD_HDX float *np22() const { return S + (13 + 4 * (pc ^ 1)) * PL; }
 };
 
 struct IterConsts {
@@ -72,120 +91,202 @@ template <int V> RVDD_HD LaneEdges lane_edges(int x0, int nx, int warp_x0)
     return e;
 }
 
-// Load row y at columns x0..x0+V (the extra column only if it exists) and run TH + primal update there.
-// `row` points at (y, x0) as an element offset; up12 / up22 hold p12 / p22 of row y-1 at the same V+1 columns
-// (zeros when y == 0).  first/last: y == 0 / y == ny-1.
-template <int V>
-RVDD_HD void eval_row(const IterPtrs &P, long long row, const LaneEdges &E, bool first, bool last, const IterConsts &K,
-                      const float (&up12)[V + 1], const float (&up22)[V + 1], RowState<V> &R)
-{
+// The inputs of one row for one lane: V own pixels plus the right neighbour (index V) of the flow, the per-warp
+// constants and the dual variable, and the left neighbour of p11 / p21.
+template <int V> struct RowIn {
     float u1[V + 1], u2[V + 1], gx[V + 1], gy[V + 1], g2[V + 1], rc[V + 1], a11[V + 1], a21[V + 1];
-    {
-        float t[V];
-        Vec<V>::ld(P.u1 + row, t);
+    float p12[V + 1], p22[V + 1];
+    float l11, l21;
+};
+
+// Load row `row` (element offset of (y, x0)) straight from global memory.
+template <int V> RVDD_HD void load_row_global(const IterPtrs &P, long long row, const LaneEdges &E, RowIn<V> &I)
+{
+    float t[V];
+    Vec<V>::ld(P.u1() + row, t);
 #pragma unroll
-        for (int j = 0; j < V; j++) u1[j] = t[j];
-        Vec<V>::ld(P.u2 + row, t);
+    for (int j = 0; j < V; j++) I.u1[j] = t[j];
+    Vec<V>::ld(P.u2() + row, t);
 #pragma unroll
-        for (int j = 0; j < V; j++) u2[j] = t[j];
-        Vec<V>::ld(P.gx + row, t);
+    for (int j = 0; j < V; j++) I.u2[j] = t[j];
+    Vec<V>::ld(P.gx() + row, t);
 #pragma unroll
-        for (int j = 0; j < V; j++) gx[j] = t[j];
-        Vec<V>::ld(P.gy + row, t);
+    for (int j = 0; j < V; j++) I.gx[j] = t[j];
+    Vec<V>::ld(P.gy() + row, t);
 #pragma unroll
-        for (int j = 0; j < V; j++) gy[j] = t[j];
-        Vec<V>::ld(P.g2 + row, t);
+    for (int j = 0; j < V; j++) I.gy[j] = t[j];
+    Vec<V>::ld(P.g2() + row, t);
 #pragma unroll
-        for (int j = 0; j < V; j++) g2[j] = t[j];
-        Vec<V>::ld(P.rc + row, t);
+    for (int j = 0; j < V; j++) I.g2[j] = t[j];
+    Vec<V>::ld(P.rc() + row, t);
 #pragma unroll
-        for (int j = 0; j < V; j++) rc[j] = t[j];
-        Vec<V>::ld(P.p11 + row, t);
+    for (int j = 0; j < V; j++) I.rc[j] = t[j];
+    Vec<V>::ld(P.p11() + row, t);
 #pragma unroll
-        for (int j = 0; j < V; j++) a11[j] = t[j];
-        Vec<V>::ld(P.p21 + row, t);
+    for (int j = 0; j < V; j++) I.a11[j] = t[j];
+    Vec<V>::ld(P.p21() + row, t);
 #pragma unroll
-        for (int j = 0; j < V; j++) a21[j] = t[j];
-        Vec<V>::ld(P.p12 + row, t);
+    for (int j = 0; j < V; j++) I.a21[j] = t[j];
+    Vec<V>::ld(P.p12() + row, t);
 #pragma unroll
-        for (int j = 0; j < V; j++) R.p12[j] = t[j];
-        Vec<V>::ld(P.p22 + row, t);
+    for (int j = 0; j < V; j++) I.p12[j] = t[j];
+    Vec<V>::ld(P.p22() + row, t);
 #pragma unroll
-        for (int j = 0; j < V; j++) R.p22[j] = t[j];
-    }
-    u1[V] = u2[V] = gx[V] = gy[V] = g2[V] = rc[V] = a11[V] = a21[V] = 0.f;
-    R.p12[V] = R.p22[V] = 0.f;
+    for (int j = 0; j < V; j++) I.p22[j] = t[j];
+    I.u1[V] = I.u2[V] = I.gx[V] = I.gy[V] = I.g2[V] = I.rc[V] = I.a11[V] = I.a21[V] = I.p12[V] = I.p22[V] = 0.f;
     if (E.right) {
         const long long q = row + V;
-        u1[V] = P.u1[q]; u2[V] = P.u2[q]; gx[V] = P.gx[q]; gy[V] = P.gy[q]; g2[V] = P.g2[q]; rc[V] = P.rc[q];
-        a11[V] = P.p11[q]; a21[V] = P.p21[q]; R.p12[V] = P.p12[q]; R.p22[V] = P.p22[q];
+        I.u1[V] = P.u1()[q]; I.u2[V] = P.u2()[q]; I.gx[V] = P.gx()[q]; I.gy[V] = P.gy()[q]; I.g2[V] = P.g2()[q]; I.rc[V] = P.rc()[q];
+        I.a11[V] = P.p11()[q]; I.a21[V] = P.p21()[q]; I.p12[V] = P.p12()[q]; I.p22[V] = P.p22()[q];
     }
-    float l11 = 0.f, l21 = 0.f;
-    if (!E.left) { l11 = P.p11[row - 1]; l21 = P.p21[row - 1]; }
+    I.l11 = I.l21 = 0.f;
+    if (!E.left) { I.l11 = P.p11()[row - 1]; I.l21 = P.p21()[row - 1]; }
+}
+
+// TH + primal update of one loaded row.  up12 / up22 hold p12 / p22 of the row above at the same V+1 columns
+// (zeros when y == 0).  first/last: y == 0 / y == ny-1.
+template <int V>
+RVDD_HD void eval_loaded(const RowIn<V> &I, const LaneEdges &E, bool first, bool last, const IterConsts &K,
+                         const float (&up12)[V + 1], const float (&up22)[V + 1], RowState<V> &R)
+{
 #pragma unroll
     for (int j = 0; j < V; j++) {
-        R.p11[j] = a11[j];
-        R.p21[j] = a21[j];
+        R.p11[j] = I.a11[j];
+        R.p21[j] = I.a21[j];
+    }
+#pragma unroll
+    for (int j = 0; j <= V; j++) {
+        R.p12[j] = I.p12[j];
+        R.p22[j] = I.p22[j];
     }
     // divergence of p: operands zeroed where the stencil leaves the image, see rvdd_div_inner
     float d1[V + 1], d2[V + 1];
 #pragma unroll
     for (int j = 0; j <= V; j++) {
         const bool lastcol = (j == V - 1) ? E.last_own : ((j == V) ? E.last_nb : false);
-        const float a1 = lastcol ? 0.f : a11[j], a2 = lastcol ? 0.f : a21[j];
-        const float b1 = last ? 0.f : R.p12[j], b2 = last ? 0.f : R.p22[j];
-        d1[j] = rvdd_div_inner(a1, j ? a11[j - 1] : l11, b1, up12[j]);
-        d2[j] = rvdd_div_inner(a2, j ? a21[j - 1] : l21, b2, up22[j]);
+        const float a1 = lastcol ? 0.f : I.a11[j], a2 = lastcol ? 0.f : I.a21[j];
+        const float b1 = last ? 0.f : I.p12[j], b2 = last ? 0.f : I.p22[j];
+        d1[j] = rvdd_div_inner(a1, j ? I.a11[j ? j - 1 : 0] : I.l11, b1, up12[j]);
+        d2[j] = rvdd_div_inner(a2, j ? I.a21[j ? j - 1 : 0] : I.l21, b2, up22[j]);
     }
     if (E.edge_warp && !first && !last) {
         // first / last column of a middle row: the reference associates (s + b) - bu (mask.c:80-81)
         if (E.left) {
-            d1[0] = rvdd_div_edge(a11[0], R.p12[0], up12[0]);
-            d2[0] = rvdd_div_edge(a21[0], R.p22[0], up22[0]);
+            d1[0] = rvdd_div_edge(I.a11[0], I.p12[0], up12[0]);
+            d2[0] = rvdd_div_edge(I.a21[0], I.p22[0], up22[0]);
         }
         if (E.last_own) {
-            d1[V - 1] = rvdd_div_edge(-(V > 1 ? a11[V > 1 ? V - 2 : 0] : l11), R.p12[V - 1], up12[V - 1]);
-            d2[V - 1] = rvdd_div_edge(-(V > 1 ? a21[V > 1 ? V - 2 : 0] : l21), R.p22[V - 1], up22[V - 1]);
+            d1[V - 1] = rvdd_div_edge(-(V > 1 ? I.a11[V > 1 ? V - 2 : 0] : I.l11), I.p12[V - 1], up12[V - 1]);
+            d2[V - 1] = rvdd_div_edge(-(V > 1 ? I.a21[V > 1 ? V - 2 : 0] : I.l21), I.p22[V - 1], up22[V - 1]);
         }
         if (E.last_nb) {
-            d1[V] = rvdd_div_edge(-a11[V - 1], R.p12[V], up12[V]);
-            d2[V] = rvdd_div_edge(-a21[V - 1], R.p22[V], up22[V]);
+            d1[V] = rvdd_div_edge(-I.a11[V - 1], I.p12[V], up12[V]);
+            d2[V] = rvdd_div_edge(-I.a21[V - 1], I.p22[V], up22[V]);
         }
     }
+#if defined(__CUDA_ARCH__)
+    bool bad = false;
 #pragma unroll
     for (int j = 0; j <= V; j++)
-        rvdd_primal_px(u1[j], u2[j], gx[j], gy[j], g2[j], rc[j], d1[j], d2[j], K.l_t, K.theta, K.g0f, &R.n1[j], &R.n2[j]);
+        rvdd_primal_px_fast(I.u1[j], I.u2[j], I.gx[j], I.gy[j], I.g2[j], I.rc[j], d1[j], d2[j], K.l_t, K.theta, K.g0f,
+                            &R.n1[j], &R.n2[j], bad);
+    if (bad) {      // rare: some quotient could not be proven exact -> the reference-exact routine for this row
 #pragma unroll
-    for (int j = 0; j < V; j++) R.res[j] = rvdd_residual_px(R.n1[j], u1[j], R.n2[j], u2[j]);
+        for (int j = 0; j <= V; j++) {
+            const float2 n = rvdd_primal_px_slow(I.u1[j], I.u2[j], I.gx[j], I.gy[j], I.g2[j], I.rc[j], d1[j], d2[j],
+                                                 K.l_t, K.theta, K.g0f);
+            R.n1[j] = n.x;
+            R.n2[j] = n.y;
+        }
+    }
+#else
+#pragma unroll
+    for (int j = 0; j <= V; j++)
+        rvdd_primal_px(I.u1[j], I.u2[j], I.gx[j], I.gy[j], I.g2[j], I.rc[j], d1[j], d2[j], K.l_t, K.theta, K.g0f,
+                       &R.n1[j], &R.n2[j]);
+#endif
+#pragma unroll
+    for (int j = 0; j < V; j++) R.res[j] = rvdd_residual_px(R.n1[j], I.u1[j], R.n2[j], I.u2[j]);
+}
+
+template <int V>
+RVDD_HD void eval_row(const IterPtrs &P, long long row, const LaneEdges &E, bool first, bool last, const IterConsts &K,
+                      const float (&up12)[V + 1], const float (&up22)[V + 1], RowState<V> &R)
+{
+    RowIn<V> I;
+    load_row_global<V>(P, row, E, I);
+    eval_loaded<V>(I, E, first, last, K, up12, up22, R);
 }
 
 // Dual update of row `cur` (its forward differences need the new flow of the row below, `nxt`), stores of the new
 // flow and dual variable, residual accumulation.
 template <int V>
 RVDD_HD void finish_row(const IterPtrs &P, long long row, const LaneEdges &E, bool down, const IterConsts &K,
-                        const RowState<V> &cur, const RowState<V> &nxt, double &err)
+                        const RowState<V> &cur, const RowState<V> &nxt, double &err, bool active = true)
 {
     float o11[V], o12[V], o21[V], o22[V], o1[V], o2[V];
+    float u1x[V], u2x[V], u1y[V], u2y[V];
 #pragma unroll
     for (int j = 0; j < V; j++) {
         // forward differences of the NEW flow (mask.c:98-141): zero on the last column / row
         const bool lastcol = (j == V - 1) && E.last_own;
-        const float u1x = lastcol ? 0.f : FSUB(cur.n1[j + 1], cur.n1[j]);
-        const float u2x = lastcol ? 0.f : FSUB(cur.n2[j + 1], cur.n2[j]);
-        const float u1y = down ? FSUB(nxt.n1[j], cur.n1[j]) : 0.f;
-        const float u2y = down ? FSUB(nxt.n2[j], cur.n2[j]) : 0.f;
+        u1x[j] = lastcol ? 0.f : FSUB(cur.n1[j + 1], cur.n1[j]);
+        u2x[j] = lastcol ? 0.f : FSUB(cur.n2[j + 1], cur.n2[j]);
+        u1y[j] = down ? FSUB(nxt.n1[j], cur.n1[j]) : 0.f;
+        u2y[j] = down ? FSUB(nxt.n2[j], cur.n2[j]) : 0.f;
         o11[j] = cur.p11[j]; o12[j] = cur.p12[j]; o21[j] = cur.p21[j]; o22[j] = cur.p22[j];
-        rvdd_dual_px(&o11[j], &o12[j], u1x, u1y, K.taut);
-        rvdd_dual_px(&o21[j], &o22[j], u2x, u2y, K.taut);
         o1[j] = cur.n1[j]; o2[j] = cur.n2[j];
-        err += (double)cur.res[j];
+        if (active) err += (double)cur.res[j];
     }
-    Vec<V>::st(P.nu1 + row, o1);
-    Vec<V>::st(P.nu2 + row, o2);
-    Vec<V>::st(P.np11 + row, o11);
-    Vec<V>::st(P.np12 + row, o12);
-    Vec<V>::st(P.np21 + row, o21);
-    Vec<V>::st(P.np22 + row, o22);
+#if defined(__CUDA_ARCH__)
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < V; j++) {
+        rvdd_dual_px_fast(&o11[j], &o12[j], u1x[j], u1y[j], K.taut, bad);
+        rvdd_dual_px_fast(&o21[j], &o22[j], u2x[j], u2y[j], K.taut, bad);
+    }
+    if (bad) {      // rare: recompute the row's dual update with the reference-exact routine
+#pragma unroll
+        for (int j = 0; j < V; j++) {
+            const float2 a = rvdd_dual_px_slow(cur.p11[j], cur.p12[j], u1x[j], u1y[j], K.taut);
+            const float2 b = rvdd_dual_px_slow(cur.p21[j], cur.p22[j], u2x[j], u2y[j], K.taut);
+            o11[j] = a.x; o12[j] = a.y; o21[j] = b.x; o22[j] = b.y;
+        }
+    }
+#else
+#pragma unroll
+    for (int j = 0; j < V; j++) {
+        rvdd_dual_px(&o11[j], &o12[j], u1x[j], u1y[j], K.taut);
+        rvdd_dual_px(&o21[j], &o22[j], u2x[j], u2y[j], K.taut);
+    }
+#endif
+    if (!active) return;
+    Vec<V>::st(P.nu1() + row, o1);
+    Vec<V>::st(P.nu2() + row, o2);
+    Vec<V>::st(P.np11() + row, o11);
+    Vec<V>::st(P.np12() + row, o12);
+    Vec<V>::st(P.np21() + row, o21);
+    Vec<V>::st(P.np22() + row, o22);
+}
+
+// p12 / p22 of the row above the strip (zeros above the image)
+template <int V>
+RVDD_HD void load_up_row(const IterPtrs &P, long long row, int nx, int y0, const LaneEdges &E, float (&up12)[V + 1],
+                         float (&up22)[V + 1])
+{
+#pragma unroll
+    for (int j = 0; j <= V; j++) up12[j] = up22[j] = 0.f;
+    if (y0 > 0) {
+        const long long b = row - nx;
+        float t[V];
+        Vec<V>::ld(P.p12() + b, t);
+#pragma unroll
+        for (int j = 0; j < V; j++) up12[j] = t[j];
+        Vec<V>::ld(P.p22() + b, t);
+#pragma unroll
+        for (int j = 0; j < V; j++) up22[j] = t[j];
+        if (E.right) { up12[V] = P.p12()[b + V]; up22[V] = P.p22()[b + V]; }
+    }
 }
 
 // One lane's strip: columns x0..x0+V-1, rows y0..y1-1.  Returns the residual sum of those pixels.  The row loop is
@@ -195,21 +296,10 @@ RVDD_HD double iterate_strip(const IterPtrs &P, int x0, int warp_x0, int y0, int
 {
     double err = 0.0;
     const LaneEdges E = lane_edges<V>(x0, nx, warp_x0);
+
     float up12[V + 1], up22[V + 1];
-#pragma unroll
-    for (int j = 0; j <= V; j++) up12[j] = up22[j] = 0.f;
     long long row = (long long)y0 * nx + x0;
-    if (y0 > 0) {
-        const long long b = row - nx;
-        float t[V];
-        Vec<V>::ld(P.p12 + b, t);
-#pragma unroll
-        for (int j = 0; j < V; j++) up12[j] = t[j];
-        Vec<V>::ld(P.p22 + b, t);
-#pragma unroll
-        for (int j = 0; j < V; j++) up22[j] = t[j];
-        if (E.right) { up12[V] = P.p12[b + V]; up22[V] = P.p22[b + V]; }
-    }
+    load_up_row<V>(P, row, nx, y0, E, up12, up22);
     RowState<V> A, B;
     eval_row<V>(P, row, E, y0 == 0, y0 == ny - 1, K, up12, up22, A);
     int y = y0;

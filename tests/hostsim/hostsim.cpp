@@ -141,11 +141,7 @@ extern "C" int hs_tvl1flow(const float *I0, const float *I1, float *u, int nx0, 
             while (err > eps2 && it < RVDD_MAX_ITERATIONS) {
                 it++;
                 IterPtrs P;
-                P.u1 = ub[uc][0]; P.u2 = ub[uc][1];
-                P.p11 = pb[pc][0]; P.p12 = pb[pc][1]; P.p21 = pb[pc][2]; P.p22 = pb[pc][3];
-                P.nu1 = ub[uc ^ 1][0]; P.nu2 = ub[uc ^ 1][1];
-                P.np11 = pb[pc ^ 1][0]; P.np12 = pb[pc ^ 1][1]; P.np21 = pb[pc ^ 1][2]; P.np22 = pb[pc ^ 1][3];
-                P.gx = gx; P.gy = gy; P.g2 = g2; P.rc = rc;
+                P.S = Sp; P.PL = (long long)PL; P.uc = uc; P.pc = pc;
                 IterConsts K;
                 K.l_t = l_t; K.theta = theta; K.taut = taut; K.g0f = rvdd_grad_zero_f32();
                 const double tot = ((w_ & 3) == 0 && !force_scalar) ? iterate_image<4>(P, w_, h_, K, nwarps_group)

@@ -117,6 +117,19 @@ def test_dropin_cppbridge_host_call(libpath, bridge, port):
     assert np.array_equal(flow.transpose(2, 0, 1), ref)
 
 
+def test_fast_exact_primitives_selftest(bridge):
+    """The straight-line division / hypot used in the iteration are bit-identical to IEEE division and the
+    double-precision square root on ~4e8 pseudo-random operand pairs (or they declare themselves unsure)."""
+    import ctypes as C
+    cnt = (C.c_ulonglong * 6)()
+    assert bridge.lib.rvdd_selftest_fastmath(12345, 592, 3000, cnt) == 0
+    hyp_n, hyp_bad, hyp_mis, div_n, div_rej, div_mis = list(cnt)
+    print("hypot: %d trials, %.3f%% fallbacks, %d mismatches; div: %d trials, %.3f%% rejected, %d mismatches"
+          % (hyp_n, 100.0 * hyp_bad / hyp_n, hyp_mis, div_n, 100.0 * div_rej / div_n, div_mis))
+    assert hyp_n > 4e8 and hyp_mis == 0 and div_mis == 0
+    assert hyp_bad / hyp_n < 0.2 and div_rej / div_n < 0.2
+
+
 def test_gray_kernel_matches_numpy(bridge):
     seq = synth.sequence(3, 40, 64, "iso12800")
     g = bridge.gray(seq.cuda()).cpu().numpy()

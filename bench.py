@@ -217,6 +217,7 @@ def run_ours(args, rank, local_rank, world):
     clocks = sampler.finish()
     ms = e0.elapsed_time(e1)
     solver_ms = br.profile_read()
+    scale_ms = br.profile_scales()
     br.profile(False)
     br.check(dev)
     if world > 1:
@@ -288,6 +289,7 @@ def run_ours(args, rank, local_rank, world):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "iterations_per_scale_mean": iters.sum(axis=2).mean(axis=0).tolist(),
+        "ms_per_pair_at_scale": scale_ms,
         "pixel_iterations_per_pair": float(sum(nx * ny * iters[:, s].sum() for s, (nx, ny) in enumerate(sizes)) / npairs),
         "flow_checksum": checksum,
     }))

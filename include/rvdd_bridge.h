@@ -98,6 +98,9 @@ RVDD_API int rvdd_solver_status(rvdd_ctx *ctx, void *stream);
  * how many it wrote (negative on error). */
 RVDD_API int rvdd_profile(rvdd_ctx *ctx, int enable);
 RVDD_API int rvdd_profile_read(rvdd_ctx *ctx, float *solver_ms, int cap);
+/* With profiling enabled the solver also stamps %globaltimer when a pair enters each pyramid level; this returns the
+ * mean time (ms) a pair of the last launch spent at level s in ms[s] (0 = finest).  Returns the number of levels. */
+RVDD_API int rvdd_profile_scales(rvdd_ctx *ctx, float *ms, int cap);
 
 /* Test hook: run `blocks` x 256 threads x `iters` pseudo-random trials of the kernels' straight-line exact
  * division / hypot fast paths against IEEE division and the double-precision square root on the device.

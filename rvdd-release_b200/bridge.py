@@ -42,6 +42,7 @@ _SIGNATURES = {
     "rvdd_solver_status": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rvdd_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "rvdd_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
+    "rvdd_profile_scales": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
     "rvdd_selftest_fastmath": (C.c_int, [C.c_ulonglong, C.c_int, C.c_int, C.POINTER(C.c_ulonglong)]),
     "rvdd_debug_level_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "rvdd_warp_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -165,6 +166,12 @@ class Bridge:
         if n < 0:
             raise BridgeError("rvdd_profile_read failed")
         return [buf[i] for i in range(n)]
+
+    def profile_scales(self):
+        """-> mean ms a pair of the last profiled launch spent at each pyramid level (index 0 = finest)."""
+        buf = (C.c_float * TRACE_SCALES)()
+        n = self.lib.rvdd_profile_scales(self.ctx, buf, TRACE_SCALES)
+        return [buf[i] for i in range(max(n, 0))]
 
     def debug_level(self, pair, which, level, nx, ny):
         """Pyramid level of the last tvl1_flow call (test hook, rvdd_debug_level_dev)."""

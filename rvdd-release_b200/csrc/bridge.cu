@@ -151,7 +151,7 @@ struct DevBuf {
 struct rvdd_ctx {
     int device = 0, sms = 0, ctas_per_sm = 0;
     int req_groups = 0;
-    DevBuf pyr, tmp, scratch, small, table;
+    DevBuf pyr, tmp, scratch, small, table, stamps;
     // pinned staging ring for the pointer tables
     void *ring_host[RING] = {nullptr, nullptr, nullptr, nullptr};
     size_t ring_cap[RING] = {0, 0, 0, 0};
@@ -201,7 +201,7 @@ extern "C" int rvdd_destroy(rvdd_ctx *c)
 {
     if (!c) return 0;
     cudaDeviceSynchronize();
-    c->pyr.release(); c->tmp.release(); c->scratch.release(); c->small.release(); c->table.release();
+    c->stamps.release(); c->pyr.release(); c->tmp.release(); c->scratch.release(); c->small.release(); c->table.release();
     c->e_frames.release(); c->e_gray.release(); c->e_flow.release(); c->e_hw2.release(); c->e_warp.release();
     c->e_iters.release();
     for (int i = 0; i < RING; i++) {
@@ -330,6 +330,11 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
     A.flow_out = flow;
     A.scratch = (float *)c->scratch.p; A.scratch_stride = scratch_stride; A.plane = plane;
     A.iters_out = iters; A.err_out = nullptr;
+    A.scale_ns = nullptr;
+    if (c->prof) {
+        CK(c->stamps.ensure(sizeof(unsigned long long) * (size_t)K * (RVDD_MAX_SCALES + 1)));
+        A.scale_ns = (unsigned long long *)c->stamps.p;
+    }
     A.bar = bar; A.partials = partials; A.status = status;
     A.ngroups = G; A.ctas_per_group = C;
     A.spin_limit = 4000000000LL;                             // ~2 s at 2 GHz
@@ -358,6 +363,26 @@ extern "C" int rvdd_profile(rvdd_ctx *c, int enable)
     c->prof = enable != 0;
     c->prof_n = 0;
     return 0;
+}
+
+// Per-scale wall time of the last profiled solver launch, averaged over its pairs: ms[s] = time a pair spent at
+// pyramid level s (index 0 = finest).  Returns the number of scales written, negative on error.
+extern "C" int rvdd_profile_scales(rvdd_ctx *c, float *ms, int cap)
+{
+    if (!c || !c->stamps.p || c->last_pairs <= 0) return -1;
+    const int K = c->last_pairs, S = c->last_pyr.S, W = RVDD_MAX_SCALES + 1;
+    std::vector<unsigned long long> h((size_t)K * W);
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpy(h.data(), c->stamps.p, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    for (int s = 0; s < S && s < cap; s++) {
+        double acc = 0;
+        for (int k = 0; k < K; k++) {
+            const unsigned long long t0 = h[(size_t)k * W + s], t1 = s ? h[(size_t)k * W + s - 1] : h[(size_t)k * W + RVDD_MAX_SCALES];
+            acc += (double)(t1 - t0) * 1e-6;
+        }
+        ms[s] = (float)(acc / K);
+    }
+    return S < cap ? S : cap;
 }
 
 extern "C" int rvdd_profile_read(rvdd_ctx *c, float *solver_ms, int cap)

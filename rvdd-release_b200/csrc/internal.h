@@ -36,6 +36,7 @@ struct SolverArgs {
     float *err_out;                     // same shape, error at loop exit, or null
     unsigned *bar;                      // [ngroups * 32] (one counter per 128 B)
     double *partials;                   // [ngroups][2][ctas_per_group]
+    unsigned long long *scale_ns;       // optional [npairs][RVDD_MAX_SCALES + 1] globaltimer stamps (profiling)
     int *status;                        // [0]: watchdog flag
     int ngroups, ctas_per_group;
     long long spin_limit;               // watchdog, in clock64 ticks

@@ -348,6 +348,12 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
         int uc = 0, pc = 0;
 
         for (int s = A.S - 1; s >= 0; s--) {
+            if (A.scale_ns && g.cta == 0 && threadIdx.x == 0) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                A.scale_ns[(long long)pair * (RVDD_MAX_SCALES + 1) + s] = t;
+                if (s == 0) A.scale_ns[(long long)pair * (RVDD_MAX_SCALES + 1) + RVDD_MAX_SCALES] = 0ULL;
+            }
             const int nx = A.nx[s], ny = A.ny[s], n = nx * ny;
             const float *I0 = P0 + A.off[s], *I1 = P1 + A.off[s];
 
@@ -424,6 +430,11 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
                 float *o1 = A.flow_out + (long long)pair * 2 * n, *o2 = o1 + n;
                 const float *c1 = UB(uc, 0), *c2 = UB(uc, 1);
                 for (int i = gtid; i < n; i += gthreads) { o1[i] = c1[i]; o2[i] = c2[i]; }
+                if (A.scale_ns && g.cta == 0 && threadIdx.x == 0) {
+                    unsigned long long t;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                    A.scale_ns[(long long)pair * (RVDD_MAX_SCALES + 1) + RVDD_MAX_SCALES] = t;
+                }
             }
             if (!group_sync(g, &s_flag)) return;
         }

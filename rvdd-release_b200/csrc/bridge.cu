@@ -253,7 +253,9 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
 
     // ---- groups and workspace
     const int total_ctas = c->sms * c->ctas_per_sm;
-    int G = c->req_groups > 0 ? c->req_groups : (K < 8 ? K : 8);
+    // one group per pair while a group keeps at least 8 CTAs (48 warps); more pairs than that queue up behind the groups
+    int G = c->req_groups > 0 ? c->req_groups : (K < total_ctas / 8 ? K : total_ctas / 8);
+    if (G < 1) G = 1;
     if (G > K) G = K;
     if (G > total_ctas) G = total_ctas;
     const int C = total_ctas / G;

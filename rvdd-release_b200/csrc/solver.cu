@@ -181,9 +181,13 @@ __device__ __forceinline__ void tma_issue_row(const IterPtrs &P, long long rowof
     bulk_g2s(d + 9 * ST_SLOT - lo, P.p21() + rowoff - lo, b_left, bar);
 }
 
-// all lanes: wait for stage `st`, then pull this lane's pixels (+ neighbours) out of shared memory
+// all lanes: wait for stage `st`, then evaluate the staged row straight out of shared memory.  The row is consumed in
+// two halves (dual variable -> divergence, then flow + constants -> primal update) so that at most half of its 52
+// input values are live in registers at any time.
 template <int st>
-__device__ __forceinline__ void tma_take_row(TmaRing &T, int lane, const LaneEdges &E, RowIn<4> &I, int *status)
+__device__ __forceinline__ void tma_eval_row(TmaRing &T, int lane, const LaneEdges &E, bool first, bool last,
+                                             const IterConsts &K, const float (&up12)[5], const float (&up22)[5],
+                                             RowState<4> &R, int *status)
 {
     const unsigned parity = T.uses[st] & 1u;
     bool ok = mbar_try_wait(T.bar[st], parity);
@@ -196,15 +200,21 @@ __device__ __forceinline__ void tma_take_row(TmaRing &T, int lane, const LaneEdg
     }
     T.uses[st]++;
     const float *s = T.stage[st] + ST_PAD + 4 * lane;
+    RowIn<4> I;
     float4 v;
 #define TAKE(k, dst)                                                \
     v = *reinterpret_cast<const float4 *>(s + (k) * ST_SLOT);       \
     I.dst[0] = v.x; I.dst[1] = v.y; I.dst[2] = v.z; I.dst[3] = v.w; \
     I.dst[4] = E.right ? s[(k) * ST_SLOT + 4] : 0.f;
-    TAKE(0, u1) TAKE(1, u2) TAKE(2, gx) TAKE(3, gy) TAKE(4, g2) TAKE(5, rc) TAKE(6, p12) TAKE(7, p22) TAKE(8, a11) TAKE(9, a21)
-#undef TAKE
+    TAKE(6, p12) TAKE(7, p22) TAKE(8, a11) TAKE(9, a21)
     I.l11 = E.left ? 0.f : s[8 * ST_SLOT - 1];
     I.l21 = E.left ? 0.f : s[9 * ST_SLOT - 1];
+    float d1[5], d2[5];
+    eval_div<4>(I, E, first, last, up12, up22, R, d1, d2);
+    asm volatile("" ::: "memory");                  // keep the second half's shared-memory loads below this point
+    TAKE(0, u1) TAKE(1, u2) TAKE(2, gx) TAKE(3, gy) TAKE(4, g2) TAKE(5, rc)
+#undef TAKE
+    eval_primal<4>(I, K, d1, d2, R);
 }
 
 // One warp's strip with staged rows (V = 4): same arithmetic as iterate_strip<4>, different data path.
@@ -235,9 +245,7 @@ __device__ __forceinline__ double iterate_strip_tma(const IterPtrs &P, TmaRing &
     }
 
     RowState<4> A, B;
-    RowIn<4> I;
-    tma_take_row<0>(T, lane, E, I, status);
-    eval_loaded<4>(I, E, y0 == 0, y0 == ny - 1, K, up12, up22, A);
+    tma_eval_row<0>(T, lane, E, y0 == 0, y0 == ny - 1, K, up12, up22, A, status);
     __syncwarp();
     if (nr > 2 && elect_one()) tma_issue_row(P, wrow + 2LL * nx, warp_x0, nx, T.stage[0], T.bar[0]);
 
@@ -245,8 +253,7 @@ __device__ __forceinline__ double iterate_strip_tma(const IterPtrs &P, TmaRing &
     while (true) {
         bool down = (i + 1 < nr);
         if (down) {                                      // i is even here: row i+1 sits in stage 1
-            tma_take_row<1>(T, lane, E, I, status);
-            eval_loaded<4>(I, E, false, y + 2 == ny, K, A.p12, A.p22, B);
+            tma_eval_row<1>(T, lane, E, false, y + 2 == ny, K, A.p12, A.p22, B, status);
             __syncwarp();
             if (i + 3 < nr && elect_one()) tma_issue_row(P, wrow + (long long)(i + 3) * nx, warp_x0, nx, T.stage[1], T.bar[1]);
         }
@@ -255,8 +262,7 @@ __device__ __forceinline__ double iterate_strip_tma(const IterPtrs &P, TmaRing &
         if (++y >= y1) break;
         down = (i + 1 < nr);
         if (down) {                                      // i is odd here: row i+1 sits in stage 0
-            tma_take_row<0>(T, lane, E, I, status);
-            eval_loaded<4>(I, E, false, y + 2 == ny, K, B.p12, B.p22, A);
+            tma_eval_row<0>(T, lane, E, false, y + 2 == ny, K, B.p12, B.p22, A, status);
             __syncwarp();
             if (i + 3 < nr && elect_one()) tma_issue_row(P, wrow + (long long)(i + 3) * nx, warp_x0, nx, T.stage[0], T.bar[0]);
         }

@@ -145,9 +145,10 @@ template <int V> RVDD_HD void load_row_global(const IterPtrs &P, long long row, 
 
 // TH + primal update of one loaded row.  up12 / up22 hold p12 / p22 of the row above at the same V+1 columns
 // (zeros when y == 0).  first/last: y == 0 / y == ny-1.
+// Part 1 needs only the dual variable of the row (a11, a21, p12, p22, l11, l21): divergence of p.
 template <int V>
-RVDD_HD void eval_loaded(const RowIn<V> &I, const LaneEdges &E, bool first, bool last, const IterConsts &K,
-                         const float (&up12)[V + 1], const float (&up22)[V + 1], RowState<V> &R)
+RVDD_HD void eval_div(const RowIn<V> &I, const LaneEdges &E, bool first, bool last, const float (&up12)[V + 1],
+                      const float (&up22)[V + 1], RowState<V> &R, float (&d1)[V + 1], float (&d2)[V + 1])
 {
 #pragma unroll
     for (int j = 0; j < V; j++) {
@@ -160,7 +161,6 @@ RVDD_HD void eval_loaded(const RowIn<V> &I, const LaneEdges &E, bool first, bool
         R.p22[j] = I.p22[j];
     }
     // divergence of p: operands zeroed where the stencil leaves the image, see rvdd_div_inner
-    float d1[V + 1], d2[V + 1];
 #pragma unroll
     for (int j = 0; j <= V; j++) {
         const bool lastcol = (j == V - 1) ? E.last_own : ((j == V) ? E.last_nb : false);
@@ -184,6 +184,13 @@ RVDD_HD void eval_loaded(const RowIn<V> &I, const LaneEdges &E, bool first, bool
             d2[V] = rvdd_div_edge(-I.a21[V - 1], I.p22[V], up22[V]);
         }
     }
+}
+
+// Part 2 needs the flow and the per-warp constants (u1, u2, gx, gy, g2, rc): thresholding + primal update + residual.
+template <int V>
+RVDD_HD void eval_primal(const RowIn<V> &I, const IterConsts &K, const float (&d1)[V + 1], const float (&d2)[V + 1],
+                         RowState<V> &R)
+{
 #if defined(__CUDA_ARCH__)
     bool bad = false;
 #pragma unroll
@@ -207,6 +214,15 @@ RVDD_HD void eval_loaded(const RowIn<V> &I, const LaneEdges &E, bool first, bool
 #endif
 #pragma unroll
     for (int j = 0; j < V; j++) R.res[j] = rvdd_residual_px(R.n1[j], I.u1[j], R.n2[j], I.u2[j]);
+}
+
+template <int V>
+RVDD_HD void eval_loaded(const RowIn<V> &I, const LaneEdges &E, bool first, bool last, const IterConsts &K,
+                         const float (&up12)[V + 1], const float (&up22)[V + 1], RowState<V> &R)
+{
+    float d1[V + 1], d2[V + 1];
+    eval_div<V>(I, E, first, last, up12, up22, R, d1, d2);
+    eval_primal<V>(I, K, d1, d2, R);
 }
 
 template <int V>

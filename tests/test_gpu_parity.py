@@ -96,6 +96,30 @@ def test_flow_1280x720_against_oracle(bridge, port):
     assert mism == 0 and np.array_equal(flow[0], ref)
 
 
+@pytest.mark.parametrize("h,w,iso", [(1080, 1920, "iso12800"), (360, 640, "iso3200")])
+def test_flow_other_pipeline_geometries(bridge, port, h, w, iso):
+    """1920x1080 (the packed-raw grid of the 3840x2160 config, 8 scales incl. odd widths 15x9) and 640x360 (the
+    true REDS packed-raw geometry, 6 scales) against the oracle."""
+    I0, I1 = synth.gray_pair(h, w, iso)
+    ref, it_ref, _, _, _ = port.tvl1flow_traced(I0, I1, err_mode=0)
+    flow, iters = run_pairs(bridge, [(I0, I1)])
+    assert iters.shape[1] == it_ref.shape[0]
+    assert epe(flow[0], ref) <= EPE_TOL
+    assert np.array_equal(iters[0], it_ref) and np.array_equal(flow[0], ref)
+
+
+def test_flow_3840x2160_properties(bridge):
+    """Largest configured geometry (9 scales): no oracle run (minutes of CPU); size-independent properties instead --
+    finite output, the synthetic motion is recovered, the result does not depend on the batch it was computed in."""
+    seq = synth.sequence(2, 2160, 3840, "iso3200").numpy().mean(axis=3, dtype=np.float32)
+    flow, iters = run_pairs(bridge, [(seq[1], seq[0])])
+    assert iters.shape[1] == 9 and np.isfinite(flow).all()
+    inner = flow[0][:, 64:-64, 64:-64]
+    assert -4.5 < inner[0].mean() < -0.5 and 0.0 < inner[1].mean() < 3.0     # same sign as test_flow_sign_convention
+    both, _ = run_pairs(bridge, [(seq[1], seq[0]), (seq[0], seq[1])], groups=2)
+    assert np.array_equal(both[0], flow[0])
+
+
 def test_zero_motion_and_linearity_properties(bridge):
     """Size-independent properties at full size: identical frames give exactly zero flow; the flow of a pair does
     not depend on what else is in the batch."""

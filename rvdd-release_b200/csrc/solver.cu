@@ -158,8 +158,15 @@ __device__ __forceinline__ bool elect_one()
     return pred != 0;
 }
 
-// elected lane: queue the bulk copies of image row `rowoff` (= y * nx + warp_x0) into `stage`
-__device__ __forceinline__ void tma_issue_row(const IterPtrs &P, long long rowoff, int warp_x0, int nx, float *stage,
+// Source addresses of a strip's first row for the three plane families (constants gx..rc, flow u1..u2, dual p11..p22);
+// consecutive planes of a family are PL floats apart, consecutive rows nx floats.
+struct TmaSrc {
+    const float *c, *u, *p;
+    long long PL;
+};
+
+// elected lane: queue the bulk copies of the image row `delta` floats below the strip's first row into `stage`
+__device__ __forceinline__ void tma_issue_row(const TmaSrc &Q, long long delta, int warp_x0, int nx, float *stage,
                                               unsigned long long *bar)
 {
     const int main_px = min(128, nx - warp_x0);
@@ -168,17 +175,18 @@ __device__ __forceinline__ void tma_issue_row(const IterPtrs &P, long long rowof
     const unsigned b_left = b_plain + (left ? 4u * ST_PAD : 0u);
     mbar_expect_tx(bar, 8u * b_plain + 2u * b_left);
     float *d = stage + ST_PAD;
-    bulk_g2s(d + 0 * ST_SLOT, P.u1() + rowoff, b_plain, bar);
-    bulk_g2s(d + 1 * ST_SLOT, P.u2() + rowoff, b_plain, bar);
-    bulk_g2s(d + 2 * ST_SLOT, P.gx() + rowoff, b_plain, bar);
-    bulk_g2s(d + 3 * ST_SLOT, P.gy() + rowoff, b_plain, bar);
-    bulk_g2s(d + 4 * ST_SLOT, P.g2() + rowoff, b_plain, bar);
-    bulk_g2s(d + 5 * ST_SLOT, P.rc() + rowoff, b_plain, bar);
-    bulk_g2s(d + 6 * ST_SLOT, P.p12() + rowoff, b_plain, bar);
-    bulk_g2s(d + 7 * ST_SLOT, P.p22() + rowoff, b_plain, bar);
+    const float *c = Q.c + delta, *u = Q.u + delta, *p = Q.p + delta;
+    bulk_g2s(d + 0 * ST_SLOT, u, b_plain, bar);                  // u1
+    bulk_g2s(d + 1 * ST_SLOT, u + Q.PL, b_plain, bar);           // u2
+    bulk_g2s(d + 2 * ST_SLOT, c, b_plain, bar);                  // gx
+    bulk_g2s(d + 3 * ST_SLOT, c + Q.PL, b_plain, bar);           // gy
+    bulk_g2s(d + 4 * ST_SLOT, c + 2 * Q.PL, b_plain, bar);       // g2
+    bulk_g2s(d + 5 * ST_SLOT, c + 3 * Q.PL, b_plain, bar);       // rc
+    bulk_g2s(d + 6 * ST_SLOT, p + Q.PL, b_plain, bar);           // p12
+    bulk_g2s(d + 7 * ST_SLOT, p + 3 * Q.PL, b_plain, bar);       // p22
     const int lo = left ? ST_PAD : 0;    // p11 / p21 also need the pixel to the left of the warp's first
-    bulk_g2s(d + 8 * ST_SLOT - lo, P.p11() + rowoff - lo, b_left, bar);
-    bulk_g2s(d + 9 * ST_SLOT - lo, P.p21() + rowoff - lo, b_left, bar);
+    bulk_g2s(d + 8 * ST_SLOT - lo, p - lo, b_left, bar);         // p11
+    bulk_g2s(d + 9 * ST_SLOT - lo, p + 2 * Q.PL - lo, b_left, bar);   // p21
 }
 
 // all lanes: wait for stage `st`, then evaluate the staged row straight out of shared memory.  The row is consumed in
@@ -227,13 +235,15 @@ __device__ __forceinline__ double iterate_strip_tma(const IterPtrs &P, TmaRing &
     const int yend = (y1 < ny) ? y1 : ny - 1;            // last row to evaluate (the strip's halo row if any)
     const int nr = yend - y0 + 1;
     const long long wrow = (long long)y0 * nx + warp_x0;
+    TmaSrc Q;
+    Q.c = P.gx() + wrow; Q.u = P.u1() + wrow; Q.p = P.p11() + wrow; Q.PL = P.PL;
     double err = 0.0;
 
     __syncwarp();
     if (elect_one()) {
         fence_proxy_async();                             // other CTAs' stores (generic proxy) -> our bulk reads
-        tma_issue_row(P, wrow, warp_x0, nx, T.stage[0], T.bar[0]);
-        if (nr > 1) tma_issue_row(P, wrow + nx, warp_x0, nx, T.stage[1], T.bar[1]);
+        tma_issue_row(Q, 0, warp_x0, nx, T.stage[0], T.bar[0]);
+        if (nr > 1) tma_issue_row(Q, nx, warp_x0, nx, T.stage[1], T.bar[1]);
     }
     float up12[5], up22[5];
     long long row = (long long)y0 * nx + x0;
@@ -247,7 +257,7 @@ __device__ __forceinline__ double iterate_strip_tma(const IterPtrs &P, TmaRing &
     RowState<4> A, B;
     tma_eval_row<0>(T, lane, E, y0 == 0, y0 == ny - 1, K, up12, up22, A, status);
     __syncwarp();
-    if (nr > 2 && elect_one()) tma_issue_row(P, wrow + 2LL * nx, warp_x0, nx, T.stage[0], T.bar[0]);
+    if (nr > 2 && elect_one()) tma_issue_row(Q, 2LL * nx, warp_x0, nx, T.stage[0], T.bar[0]);
 
     int y = y0, i = 0;                                   // i = y - y0
     while (true) {
@@ -255,7 +265,7 @@ __device__ __forceinline__ double iterate_strip_tma(const IterPtrs &P, TmaRing &
         if (down) {                                      // i is even here: row i+1 sits in stage 1
             tma_eval_row<1>(T, lane, E, false, y + 2 == ny, K, A.p12, A.p22, B, status);
             __syncwarp();
-            if (i + 3 < nr && elect_one()) tma_issue_row(P, wrow + (long long)(i + 3) * nx, warp_x0, nx, T.stage[1], T.bar[1]);
+            if (i + 3 < nr && elect_one()) tma_issue_row(Q, (long long)(i + 3) * nx, warp_x0, nx, T.stage[1], T.bar[1]);
         }
         finish_row<4>(P, row, E, down, K, A, B, err, active);
         row += nx; ++i;
@@ -264,7 +274,7 @@ __device__ __forceinline__ double iterate_strip_tma(const IterPtrs &P, TmaRing &
         if (down) {                                      // i is odd here: row i+1 sits in stage 0
             tma_eval_row<0>(T, lane, E, false, y + 2 == ny, K, B.p12, B.p22, A, status);
             __syncwarp();
-            if (i + 3 < nr && elect_one()) tma_issue_row(P, wrow + (long long)(i + 3) * nx, warp_x0, nx, T.stage[0], T.bar[0]);
+            if (i + 3 < nr && elect_one()) tma_issue_row(Q, (long long)(i + 3) * nx, warp_x0, nx, T.stage[0], T.bar[0]);
         }
         finish_row<4>(P, row, E, down, K, B, A, err, active);
         row += nx; ++i;

@@ -195,6 +195,24 @@ def test_warp_against_oracle_sizes(bridge, C, H, W):
     assert np.array_equal(m.cpu().numpy(), mref.numpy())
 
 
+@pytest.mark.parametrize("C,H,W,interp", [(3, 360, 640, "bicubic"), (48, 90, 200, "bicubic"), (5, 77, 131, "bilinear"),
+                                            (11, 64, 96, "bicubic")])
+def test_warp_smooth_flow_staged_path(bridge, C, H, W, interp):
+    """Smooth flows (what TV-L1 produces) take the shared-memory staged path of the tiled kernel, including tiles at
+    the image border where taps are clamped; large constant shifts push whole tiles out of the image."""
+    from rvdd_release_b200 import flow_utils
+    g = torch.Generator().manual_seed(H)
+    x = torch.randn(2, C, H, W, generator=g)
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    f0 = torch.stack((2.5 + 1.5 * torch.sin(yy / 17.0), -1.5 + torch.cos(xx / 23.0)), 0)
+    f1 = torch.stack((-40.0 + 0.01 * xx, 25.0 + 0.02 * yy), 0)             # far outside on two sides
+    flow = torch.stack((f0, f1), 0)
+    ref, mref = warp_ref.warp(x, flow, interp)
+    y, m = flow_utils.warp(x.cuda(), flow.cuda(), interp)
+    assert rel_err(y.cpu().numpy(), ref.numpy()) <= WARP_RTOL
+    assert np.array_equal(m.cpu().numpy(), mref.numpy())
+
+
 def test_warp_channel_slice_and_identity(bridge):
     """The feature-recurrence call site warps a channel slice of a bigger tensor (recurrent_model.py:295-297);
     zero flow is the identity up to the normalise / un-normalise round trip of the sampling grid, which the

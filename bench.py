@@ -81,6 +81,20 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one solver launch of this very workload (29 pairs), from the
+    committed `ncu --set full` capture (profiles/solver_kernel_r01.txt); None if the summary is missing."""
+    try:
+        tot = 0.0
+        for line in open(os.path.join(ROOT, "profiles", "solver_kernel_r01.txt")):
+            f = line.split()
+            if f and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
+        return tot or None
+    except Exception:
+        return None
+
+
 def solver_bytes(sizes, iters, nwarps=5):
     """Algorithmic bytes of one solver launch: per pair and scale 3N (centred gradient) +
     10N per warp (bicubic warp constants) + 16N per inner iteration (64 B/pixel) + 2(N_s + N_{s-1}) flow upsampling,
@@ -119,6 +133,11 @@ def cpu_reference(frames_np, pairs, threads):
     except Exception:
         lib, kind = PortLib(), "port"
     torch.set_num_threads(threads)
+    try:        # torchrun exports OMP_NUM_THREADS=1 before the OpenMP runtime starts; ask it for all cores explicitly
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(threads))
+    except OSError:
+        pass
     t0 = time.perf_counter()
     for s, t in pairs:
         i0 = np.ascontiguousarray(np.mean(frames_np[t], axis=2))
@@ -258,7 +277,8 @@ def run_ours(args, rank, local_rank, world):
     avg_solver_ms = sum(solver_ms) / max(1, len(solver_ms))
     achieved = sb / (avg_solver_ms * 1e-3) / 1e9 if avg_solver_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "rvdd::solver_kernel (persistent TV-L1 solver, 1 launch per step)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
+                "traffic_source": "profiles/solver_kernel_r01.txt (ncu --set full of this workload, per launch)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": sb, "avg_launch_ms": avg_solver_ms,
                 "share_of_step": avg_solver_ms * args.steps / ms if ms > 0 else None,
                 "step_algorithmic_bytes": step_bytes(sizes, iters),
@@ -267,7 +287,7 @@ def run_ours(args, rank, local_rank, world):
     # ---- CPU baseline: the reference C on this box's cores, bounded sample of the same workload
     threads = os.cpu_count() or 1
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         fr = h_frames[:3].numpy()
         dt, kind = cpu_reference(fr, [(0, 1), (1, 2)], threads)
         cpu = {"value": 2 / dt, "unit": "pairs/s", "cores": threads, "kind": kind,

@@ -81,3 +81,27 @@ def compute_flow_and_warp(iio_img1, iio_img2, flow_type='tvl1', interpolation='b
 def upsample_factor_2(downsampled_batch, multiply_by=1.):
     """[..., C, H, W] -> [..., C, 2H, 2W], bilinear, align_corners=True, times multiply_by (flow_utils.py:159-174)."""
     return _bridge.default_bridge().upsample2(downsampled_batch, multiply_by)
+
+
+def remosaick(x):
+    """RGB [B, 3, 2H, 2W] -> packed 'gbrg' raw [B, 4, H, W] (util/Hamilton_Adam_demo.py:237-246)."""
+    return torch.stack((x[:, 1, 0::2, 0::2], x[:, 2, 0::2, 1::2], x[:, 0, 1::2, 0::2], x[:, 1, 1::2, 1::2]), dim=1)
+
+
+def compute_flows_from_denoised(denoised, noisy_packed, predemosaic=True):
+    """Online flow from the previous DENOISED frame to the current noisy frame, entirely on the GPU -- the
+    ``--val_flow_from_denoised`` path of the reference (validate.py:16-38), which moves the denoised frame to the
+    CPU, remosaicks it, calls the C TV-L1 and moves the flow back, every frame.
+
+    denoised     : CUDA tensor [1, 3, 2H, 2W] (or [1, 4, H, W] with predemosaic=False) in the network's [-1, 1] range
+    noisy_packed : CUDA tensor [1, 4, H, W], the current noisy packed-raw frame (data['n'][0, -4:]) in [-1, 1]
+    returns      : [1, 1, 2, H, W] flow (source = denoised frame, target = noisy frame), the layout of data['flow']
+    """
+    b = _bridge.default_bridge()
+    src = remosaick(denoised) if predemosaic else denoised
+    # singleiT of library.py:67: (x + 1) / 2, CHW -> HWC
+    pair = torch.cat((noisy_packed[:1], src[:1]), 0)
+    pair = ((pair + 1.) / 2.).permute(0, 2, 3, 1).contiguous()
+    gray = b.gray(pair)                                          # mean of the 4 channels (library.py:165-167)
+    flow = b.tvl1_flow(gray, src=[1], tgt=[0])                   # target = noisy frame, source = denoised frame
+    return flow.unsqueeze(0)

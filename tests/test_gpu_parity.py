@@ -250,3 +250,25 @@ def test_single_warp_and_compute_flow_and_warp(libpath, bridge, port):
     ref2 = port.tvl1flow(np.mean(seq[1], axis=2), np.mean(seq[2], axis=2)).transpose(1, 2, 0)
     assert np.array_equal(f[1].numpy(), ref2)
     assert int(it[0].sum()) > 0
+
+
+def test_online_flow_from_denoised_frame(bridge, port):
+    """validate.py:16-38 (--val_flow_from_denoised) without the GPU -> CPU -> GPU round trip: remosaick + gray +
+    TV-L1 on the device against the same steps done the reference's way on the host."""
+    from rvdd_release_b200 import flow_utils
+    seq = synth.sequence(2, 60, 96, "iso3200")
+    noisy = (seq[1] / 4095.0 * 2 - 1).permute(2, 0, 1)[None].contiguous()              # T: 2x - 1, CHW
+    g = torch.Generator().manual_seed(3)
+    den = torch.rand(1, 3, 120, 192, generator=g) * 2 - 1                               # a "denoised" RGB frame
+    den[:, 1, 0::2, 0::2] = (seq[0][:, :, 0] / 4095.0 * 2 - 1)                          # make it resemble frame t-1
+    den[:, 2, 0::2, 1::2] = (seq[0][:, :, 1] / 4095.0 * 2 - 1)
+    den[:, 0, 1::2, 0::2] = (seq[0][:, :, 2] / 4095.0 * 2 - 1)
+    den[:, 1, 1::2, 1::2] = (seq[0][:, :, 3] / 4095.0 * 2 - 1)
+    flow = flow_utils.compute_flows_from_denoised(den.cuda(), noisy.cuda())
+    assert tuple(flow.shape) == (1, 1, 2, 60, 96)
+    # host restatement: remosaick (Hamilton_Adam_demo.py:237-246), singleiT (library.py:67), mean of 4, tvl1flow
+    y = torch.stack((den[:, 1, 0::2, 0::2], den[:, 2, 0::2, 1::2], den[:, 0, 1::2, 0::2], den[:, 1, 1::2, 1::2]), 1)
+    img1 = ((y[0] + 1.) / 2.).permute(1, 2, 0).numpy()
+    img2 = ((noisy[0] + 1.) / 2.).permute(1, 2, 0).numpy()
+    ref = port.tvl1flow(np.mean(img2, axis=2), np.mean(img1, axis=2))
+    assert np.array_equal(flow[0, 0].cpu().numpy(), ref)

@@ -143,6 +143,17 @@ RVDD_API int rvdd_flow_and_warp_host(rvdd_ctx *ctx, const float *frames_host, in
                             const int *src, const int *tgt, int npairs, const rvdd_tvl1_params *params,
                             float *flow_host, float *warped_host, int *iters_host);
 
+/* The same work as rvdd_flow_and_warp_host, split into submit + wait over two staging slots (0, 1) so that a stream
+ * of batches (e.g. one video after another in the offline precompute, base_dataset.py:143-189) keeps three CUDA
+ * streams busy: batch i+1 uploads while batch i computes and batch i-1 downloads.  Host buffers must be pinned for
+ * the copies to overlap and must stay untouched until the slot has been waited for.  A slot has to be waited for
+ * before it is submitted again. */
+RVDD_API int rvdd_flow_and_warp_host_submit(rvdd_ctx *ctx, int slot, const float *frames_host, int nframes, int h, int w,
+                                            int c, const int *src, const int *tgt, int npairs,
+                                            const rvdd_tvl1_params *params, float *flow_host, float *warped_host,
+                                            int *iters_host);
+RVDD_API int rvdd_flow_and_warp_host_wait(rvdd_ctx *ctx, int slot);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,10 @@ _SIGNATURES = {
     "rvdd_flow_and_warp_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                           C.c_void_p, C.c_int, C.POINTER(TVL1Params), C.c_void_p, C.c_void_p,
                                           C.c_void_p]),
+    "rvdd_flow_and_warp_host_submit": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                 C.c_void_p, C.c_void_p, C.c_int, C.POINTER(TVL1Params), C.c_void_p,
+                                                 C.c_void_p, C.c_void_p]),
+    "rvdd_flow_and_warp_host_wait": (C.c_int, [C.c_void_p, C.c_int]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -243,6 +247,22 @@ class Bridge:
                                                   flow.data_ptr(), warped.data_ptr() if want_warp else None,
                                                   iters.data_ptr() if trace else None))
         return flow, warped, iters
+
+
+    def submit_host(self, slot, frames, src, tgt, flow_out, warped_out=None, params=None):
+        """Asynchronous half of flow_and_warp_host on staging slot 0 / 1 (rvdd_flow_and_warp_host_submit).  `frames`,
+        `flow_out`, `warped_out` are CPU float32 tensors (pin them to let the copies overlap) that must stay alive and
+        untouched until wait_host(slot)."""
+        n, h, w, c = frames.shape
+        src = np.ascontiguousarray(src, dtype=np.int32)
+        tgt = np.ascontiguousarray(tgt, dtype=np.int32)
+        self._ck(self.lib.rvdd_flow_and_warp_host_submit(
+            self.ctx, int(slot), frames.data_ptr(), n, h, w, c, src.ctypes.data, tgt.ctypes.data, int(src.size),
+            C.byref(params) if params else None, flow_out.data_ptr(),
+            warped_out.data_ptr() if warped_out is not None else None, None))
+
+    def wait_host(self, slot):
+        self._ck(self.lib.rvdd_flow_and_warp_host_wait(self.ctx, int(slot)))
 
 
 _DEFAULT = None

@@ -161,7 +161,11 @@ struct rvdd_ctx {
     Pyramid last_pyr;                   // geometry of the last rvdd_tvl1_flow_dev call (for rvdd_debug_level_dev)
     int last_pairs = 0;
     // end-to-end staging (rvdd_flow_and_warp_host, tvl1flow)
-    DevBuf e_frames, e_gray, e_flow, e_hw2, e_warp, e_iters;
+    DevBuf e_frames, e_gray, e_flow, e_hw2, e_warp, e_iters;    // slot 0 (also used by tvl1flow)
+    DevBuf f_frames, f_gray, f_flow, f_hw2, f_warp, f_iters;    // slot 1 (pipelined submissions)
+    cudaEvent_t slot_in[2] = {nullptr, nullptr}, slot_compute[2] = {nullptr, nullptr}, slot_done[2] = {nullptr, nullptr};
+    int *slot_status_host[2] = {nullptr, nullptr};               // pinned: solver watchdog word of the slot's launch
+    bool slot_busy[2] = {false, false};
     cudaStream_t st_compute = nullptr, st_in = nullptr, st_out = nullptr;
     std::vector<cudaEvent_t> events;
     // optional timing of the solver launches (rvdd_profile / rvdd_profile_read)
@@ -190,6 +194,13 @@ extern "C" int rvdd_create(rvdd_ctx **out)
         return fail("rvdd_create: solver kernel does not fit on this device", e);
     }
     for (int i = 0; i < RING; i++) CK(cudaEventCreateWithFlags(&c->ring_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) {
+        CK(cudaEventCreateWithFlags(&c->slot_in[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->slot_compute[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->slot_done[i], cudaEventDisableTiming));
+        CK(cudaMallocHost((void **)&c->slot_status_host[i], sizeof(int)));
+        *c->slot_status_host[i] = 0;
+    }
     CK(cudaStreamCreateWithFlags(&c->st_compute, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking));
@@ -204,6 +215,13 @@ extern "C" int rvdd_destroy(rvdd_ctx *c)
     c->stamps.release(); c->pyr.release(); c->tmp.release(); c->scratch.release(); c->small.release(); c->table.release();
     c->e_frames.release(); c->e_gray.release(); c->e_flow.release(); c->e_hw2.release(); c->e_warp.release();
     c->e_iters.release();
+    c->f_frames.release(); c->f_gray.release(); c->f_flow.release(); c->f_hw2.release(); c->f_warp.release(); c->f_iters.release();
+    for (int i = 0; i < 2; i++) {
+        if (c->slot_in[i]) cudaEventDestroy(c->slot_in[i]);
+        if (c->slot_compute[i]) cudaEventDestroy(c->slot_compute[i]);
+        if (c->slot_done[i]) cudaEventDestroy(c->slot_done[i]);
+        if (c->slot_status_host[i]) cudaFreeHost(c->slot_status_host[i]);
+    }
     for (int i = 0; i < RING; i++) {
         if (c->ring_host[i]) cudaFreeHost(c->ring_host[i]);
         if (c->ring_ev[i]) cudaEventDestroy(c->ring_ev[i]);
@@ -469,41 +487,42 @@ __global__ void interleave_kernel(const float *__restrict__ planar, float2 *__re
         hw2[k * n + i] = make_float2(p[i], p[n + i]);
 }
 
-extern "C" int rvdd_flow_and_warp_host(rvdd_ctx *c, const float *frames, int nframes, int h, int w, int ch,
-                                       const int *src, const int *tgt, int npairs, const rvdd_tvl1_params *params,
-                                       float *flow_host, float *warped_host, int *iters_host)
+// Three-stage pipeline over two staging slots: uploads on st_in, kernels on st_compute, downloads on st_out, chained
+// with events.  While slot s computes, the other slot can already upload its frames and the previous submission of
+// slot s^1 can still be downloading -- for a stream of sequences (the offline precompute) the copies disappear behind
+// the solver.  A slot must be waited for before it is submitted again.
+extern "C" int rvdd_flow_and_warp_host_submit(rvdd_ctx *c, int slot, const float *frames, int nframes, int h, int w, int ch,
+                                              const int *src, const int *tgt, int npairs, const rvdd_tvl1_params *params,
+                                              float *flow_host, float *warped_host, int *iters_host)
 {
-    if (!c) return fail("rvdd_flow_and_warp_host: null context");
+    if (!c) return fail("rvdd_flow_and_warp_host_submit: null context");
+    if (slot != 0 && slot != 1) return fail("rvdd_flow_and_warp_host_submit: slot must be 0 or 1");
+    if (c->slot_busy[slot]) return fail("rvdd_flow_and_warp_host_submit: slot still in flight (call ..._wait first)");
     if (npairs <= 0) return 0;
-    if (!frames || !src || !tgt || !flow_host) return fail("rvdd_flow_and_warp_host: null argument");
-    if (ch != 1 && ch != 3 && ch != 4) return fail("rvdd_flow_and_warp_host: channels must be 1, 3 or 4");
+    if (!frames || !src || !tgt || !flow_host) return fail("rvdd_flow_and_warp_host_submit: null argument");
+    if (ch != 1 && ch != 3 && ch != 4) return fail("rvdd_flow_and_warp_host_submit: channels must be 1, 3 or 4");
     const long long n = (long long)h * w;
     const rvdd_tvl1_params p = sanitize(params);
+    DevBuf &b_frames = slot ? c->f_frames : c->e_frames, &b_gray = slot ? c->f_gray : c->e_gray;
+    DevBuf &b_flow = slot ? c->f_flow : c->e_flow, &b_hw2 = slot ? c->f_hw2 : c->e_hw2;
+    DevBuf &b_warp = slot ? c->f_warp : c->e_warp, &b_iters = slot ? c->f_iters : c->e_iters;
+    CK(b_frames.ensure(sizeof(float) * (size_t)nframes * n * ch));
+    CK(b_gray.ensure(sizeof(float) * (size_t)nframes * n));
+    CK(b_flow.ensure(sizeof(float) * (size_t)npairs * 2 * n));
+    CK(b_hw2.ensure(sizeof(float) * (size_t)npairs * 2 * n));
+    if (warped_host) CK(b_warp.ensure(sizeof(float) * (size_t)npairs * n * ch));
+    if (iters_host) CK(b_iters.ensure(sizeof(int) * (size_t)npairs * RVDD_TRACE_SCALES * p.nwarps));
+    float *d_frames = (float *)b_frames.p, *d_gray = (float *)b_gray.p, *d_flow = (float *)b_flow.p;
+    float *d_hw2 = (float *)b_hw2.p, *d_warp = (float *)b_warp.p;
+    int *d_iters = iters_host ? (int *)b_iters.p : nullptr;
     cudaStream_t st = c->st_compute;
-    CK(c->e_frames.ensure(sizeof(float) * (size_t)nframes * n * ch));
-    CK(c->e_gray.ensure(sizeof(float) * (size_t)nframes * n));
-    CK(c->e_flow.ensure(sizeof(float) * (size_t)npairs * 2 * n));
-    CK(c->e_hw2.ensure(sizeof(float) * (size_t)npairs * 2 * n));
-    if (warped_host) CK(c->e_warp.ensure(sizeof(float) * (size_t)npairs * n * ch));
-    if (iters_host) CK(c->e_iters.ensure(sizeof(int) * (size_t)npairs * RVDD_TRACE_SCALES * p.nwarps));
-    float *d_frames = (float *)c->e_frames.p, *d_gray = (float *)c->e_gray.p, *d_flow = (float *)c->e_flow.p;
-    float *d_hw2 = (float *)c->e_hw2.p, *d_warp = (float *)c->e_warp.p;
-    int *d_iters = iters_host ? (int *)c->e_iters.p : nullptr;
 
-    // events: one per frame (upload done) + one (compute done)
-    while ((int)c->events.size() < nframes + 1) {
-        cudaEvent_t ev;
-        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        c->events.push_back(ev);
-    }
-    // upload frame by frame on the copy-in stream; gray conversion follows each frame on the compute stream
-    for (int f = 0; f < nframes; f++) {
-        CK(cudaMemcpyAsync(d_frames + (long long)f * n * ch, frames + (long long)f * n * ch, sizeof(float) * n * ch,
-                           cudaMemcpyHostToDevice, c->st_in));
-        CK(cudaEventRecord(c->events[f], c->st_in));
-        CK(cudaStreamWaitEvent(st, c->events[f], 0));
-        CK(launch_gray(d_frames + (long long)f * n * ch, d_gray + (long long)f * n, n, ch, st));
-    }
+    // stage 1: upload
+    CK(cudaMemcpyAsync(d_frames, frames, sizeof(float) * (size_t)nframes * n * ch, cudaMemcpyHostToDevice, c->st_in));
+    CK(cudaEventRecord(c->slot_in[slot], c->st_in));
+    // stage 2: gray, TV-L1, (h, w, 2) interleave, warp of the source frames
+    CK(cudaStreamWaitEvent(st, c->slot_in[slot], 0));
+    CK(launch_gray(d_frames, d_gray, (long long)nframes * n, ch, st));
     int rc = rvdd_tvl1_flow_dev(c, d_gray, nframes, w, h, src, tgt, npairs, &p, d_flow, d_iters, st);
     if (rc) return rc;
     {
@@ -512,7 +531,6 @@ extern "C" int rvdd_flow_and_warp_host(rvdd_ctx *c, const float *frames, int nfr
         interleave_kernel<<<dim3(bx, npairs), 256, 0, st>>>(d_flow, (float2 *)d_hw2, n);
         CK(cudaGetLastError());
     }
-    CK(cudaMemcpyAsync(flow_host, d_hw2, sizeof(float) * (size_t)npairs * 2 * n, cudaMemcpyDeviceToHost, st));
     if (warped_host) {
         // single_warp(img1 = source frame, flow) in the frames' own HWC layout (flow_utils.py:105-122, :154)
         for (int k = 0; k < npairs; k++) {
@@ -526,14 +544,46 @@ extern "C" int rvdd_flow_and_warp_host(rvdd_ctx *c, const float *frames, int nfr
             a.fh = h; a.fw = w; a.flow_mul = 1.0f; a.interp = 1;
             CK(launch_warp(a, st));
         }
-        CK(cudaMemcpyAsync(warped_host, d_warp, sizeof(float) * (size_t)npairs * n * ch, cudaMemcpyDeviceToHost, st));
     }
+    CK(cudaMemcpyAsync(c->slot_status_host[slot], c->status_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(c->slot_compute[slot], st));
+    // stage 3: download
+    CK(cudaStreamWaitEvent(c->st_out, c->slot_compute[slot], 0));
+    CK(cudaMemcpyAsync(flow_host, d_hw2, sizeof(float) * (size_t)npairs * 2 * n, cudaMemcpyDeviceToHost, c->st_out));
+    if (warped_host)
+        CK(cudaMemcpyAsync(warped_host, d_warp, sizeof(float) * (size_t)npairs * n * ch, cudaMemcpyDeviceToHost, c->st_out));
     if (iters_host)
         CK(cudaMemcpyAsync(iters_host, d_iters, sizeof(int) * (size_t)npairs * RVDD_TRACE_SCALES * p.nwarps,
-                           cudaMemcpyDeviceToHost, st));
-    int rs = rvdd_solver_status(c, st);   // synchronises the compute stream
-    if (rs) return rs;
+                           cudaMemcpyDeviceToHost, c->st_out));
+    CK(cudaEventRecord(c->slot_done[slot], c->st_out));
+    // the next submission of the OTHER slot may overwrite the shared TV-L1 workspace only after this one's kernels:
+    // all kernels run on st_compute, so stream order already guarantees it.
+    c->slot_busy[slot] = true;
     return 0;
+}
+
+extern "C" int rvdd_flow_and_warp_host_wait(rvdd_ctx *c, int slot)
+{
+    if (!c) return fail("rvdd_flow_and_warp_host_wait: null context");
+    if (slot != 0 && slot != 1) return fail("rvdd_flow_and_warp_host_wait: slot must be 0 or 1");
+    if (!c->slot_busy[slot]) return 0;
+    CK(cudaEventSynchronize(c->slot_done[slot]));
+    c->slot_busy[slot] = false;
+    if (*c->slot_status_host[slot]) return fail("solver watchdog fired: a group barrier timed out, results are invalid");
+    return 0;
+}
+
+extern "C" int rvdd_flow_and_warp_host(rvdd_ctx *c, const float *frames, int nframes, int h, int w, int ch,
+                                       const int *src, const int *tgt, int npairs, const rvdd_tvl1_params *params,
+                                       float *flow_host, float *warped_host, int *iters_host)
+{
+    if (!c) return fail("rvdd_flow_and_warp_host: null context");
+    int rc = rvdd_flow_and_warp_host_wait(c, 0);
+    if (rc) return rc;
+    rc = rvdd_flow_and_warp_host_submit(c, 0, frames, nframes, h, w, ch, src, tgt, npairs, params, flow_host, warped_host,
+                                        iters_host);
+    if (rc) return rc;
+    return rvdd_flow_and_warp_host_wait(c, 0);
 }
 
 // The reference symbol (libBridge.cpp:44): host float buffers, default parameters, planar (u, v) result.

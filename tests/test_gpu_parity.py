@@ -272,3 +272,27 @@ def test_online_flow_from_denoised_frame(bridge, port):
     img2 = ((noisy[0] + 1.) / 2.).permute(1, 2, 0).numpy()
     ref = port.tvl1flow(np.mean(img2, axis=2), np.mean(img1, axis=2))
     assert np.array_equal(flow[0, 0].cpu().numpy(), ref)
+
+
+def test_pipelined_host_submissions(bridge, port):
+    """rvdd_flow_and_warp_host_submit / _wait: two batches in flight on the two staging slots give the same bits as the
+    blocking call; resubmitting a busy slot is refused."""
+    from rvdd_release_b200.bridge import BridgeError
+    seqs = [synth.sequence(3, 64, 96, iso, noise_seed=7 * i) for i, iso in enumerate(("iso3200", "iso12800", "clean"))]
+    src, tgt = [0, 1], [1, 2]
+    want = [bridge.flow_and_warp_host(s, src, tgt)[:2] for s in seqs]
+    frames = [s.pin_memory() for s in seqs]
+    flows = [torch.empty((2, 64, 96, 2)).pin_memory() for _ in seqs]
+    warps = [torch.empty((2, 64, 96, 4)).pin_memory() for _ in seqs]
+    bridge.submit_host(0, frames[0], src, tgt, flows[0], warps[0])
+    bridge.submit_host(1, frames[1], src, tgt, flows[1], warps[1])
+    with pytest.raises(BridgeError):
+        bridge.submit_host(0, frames[2], src, tgt, flows[2], warps[2])
+    bridge.wait_host(0)
+    bridge.submit_host(0, frames[2], src, tgt, flows[2], warps[2])
+    bridge.wait_host(1)
+    bridge.wait_host(0)
+    for k in range(3):
+        assert torch.equal(flows[k], want[k][0]) and torch.equal(warps[k], want[k][1])
+    g = np.mean(seqs[1].numpy(), axis=3)
+    assert np.array_equal(flows[1][0].numpy().transpose(2, 0, 1), port.tvl1flow(g[1], g[0]))

@@ -242,6 +242,33 @@ extern "C" int rvdd_set_groups(rvdd_ctx *c, int n)
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ TMA descriptors
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// scratch viewed as [nplanes][plane] floats; box = `box_planes` adjacent planes x 136 consecutive floats
+static int encode_scratch_map(CUtensorMap *tm, float *scratch, long long plane, long long nplanes, int box_planes)
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p)
+            return fail("cuTensorMapEncodeTiled not available from this driver");
+        fn = (EncodeTiledFn)p;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)plane, (cuuint64_t)nplanes};
+    const cuuint64_t strides[1] = {(cuuint64_t)plane * sizeof(float)};
+    const cuuint32_t box[2] = {136u, (cuuint32_t)box_planes};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, scratch, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed");
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ TV-L1 driver
 
 extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, int nx, int ny, const int *src,
@@ -349,6 +376,8 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
     A.pyr0 = pyr; A.pyr1 = pyr + (long long)K * P.total; A.pyr_stride = P.total;
     A.flow_out = flow;
     A.scratch = (float *)c->scratch.p; A.scratch_stride = scratch_stride; A.plane = plane;
+    if (encode_scratch_map(&A.tm4, A.scratch, plane, 18LL * G, 4)) return -1;
+    if (encode_scratch_map(&A.tm2, A.scratch, plane, 18LL * G, 2)) return -1;
     A.iters_out = iters; A.err_out = nullptr;
     A.scale_ns = nullptr;
     if (c->prof) {

@@ -1,5 +1,6 @@
 // internal.h -- host-side declarations shared by the .cu files of libBridge.so (not part of the C ABI).
 #pragma once
+#include <cuda.h>            // CUtensorMap (type only; the encoder is fetched with cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -22,6 +23,10 @@ struct GaussTaps {
 
 // Arguments of the persistent solver kernel (solver.cu).
 struct SolverArgs {
+    // TMA descriptors of the whole solver scratch viewed as a 2-D tensor [ngroups * 18 planes][plane floats]; the
+    // boxes are one staged row segment (136 floats) of 4 adjacent planes (constants, dual variable) or 2 (flow).
+    alignas(64) CUtensorMap tm4;
+    alignas(64) CUtensorMap tm2;
     int npairs, S, fscale, nwarps;
     int nx[RVDD_MAX_SCALES], ny[RVDD_MAX_SCALES];
     long long off[RVDD_MAX_SCALES];

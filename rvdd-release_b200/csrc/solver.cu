@@ -110,18 +110,29 @@ __device__ __forceinline__ double group_sum(const GroupCtx &g, int slot, double 
 
 #define ST_PAD 4                         // pixels staged on either side of the warp's 128
 #define ST_SLOT (128 + 2 * ST_PAD)       // floats per array per row (544 B, a multiple of 16 B)
-#define ST_ROW (10 * ST_SLOT)            // floats per staged row
+// One staged row = three TMA boxes, each landing at a 128-byte aligned offset of the stage:
+//   [gx gy g2 rc] (4 planes) at float 0, [u1 u2] at float 544, [p11 p12 p21 p22] at float 832
+#define ST_OFF_C 0
+#define ST_OFF_U (4 * ST_SLOT)
+#define ST_OFF_P 832
+#define ST_ROW 1408                      // floats per stage (5632 B, a multiple of 128 B)
 #ifndef ST_STAGES
 #define ST_STAGES 2
 #endif
-#define ST_WARP_BYTES (ST_STAGES * ST_ROW * 4 + 64)   // + the mbarriers
+#define ST_WARP_BYTES (ST_STAGES * ST_ROW * 4 + 128)  // + the mbarriers; keeps every warp's stages 128-byte aligned
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
+// Per-warp ring of ST_STAGES staged rows.  Rows are issued and consumed strictly in order, so two running counters say
+// everything: row number n lives in stage n % ST_STAGES and completes that stage's mbarrier phase (n / ST_STAGES) & 1.
 struct TmaRing {
-    float *stage[ST_STAGES];
-    unsigned long long *bar[ST_STAGES];
-    unsigned uses[ST_STAGES];            // completed uses of each stage (phase parity = uses & 1)
+    unsigned char *base;                 // stage k at base + k * ST_ROW * 4, mbarrier k at base + ST_STAGES * ST_ROW * 4 + 16 k
+    unsigned issued, taken;
+    __device__ __forceinline__ float *stage(unsigned k) const { return reinterpret_cast<float *>(base + (size_t)k * ST_ROW * 4); }
+    __device__ __forceinline__ unsigned long long *bar(unsigned k) const
+    {
+        return reinterpret_cast<unsigned long long *>(base + (size_t)ST_STAGES * ST_ROW * 4 + 16 * k);
+    }
 };
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
@@ -158,76 +169,74 @@ __device__ __forceinline__ bool elect_one()
     return pred != 0;
 }
 
-// Source addresses of a strip's first row for the three plane families (constants gx..rc, flow u1..u2, dual p11..p22);
-// consecutive planes of a family are PL floats apart, consecutive rows nx floats.
+// Row coordinates of a strip for the tensor-map copies: c0 = linear float index of (y, warp_x0 - ST_PAD) inside a plane,
+// plane rows of the three families in the [ngroups * 18][plane] view of the scratch.
 struct TmaSrc {
-    const float *c, *u, *p;
-    long long PL;
+    int c0, row_c, row_u, row_p;
 };
 
-// elected lane: queue the bulk copies of the image row `delta` floats below the strip's first row into `stage`
-__device__ __forceinline__ void tma_issue_row(const TmaSrc &Q, long long delta, int warp_x0, int nx, float *stage,
-                                              unsigned long long *bar)
+__device__ __forceinline__ void tma_box(const CUtensorMap *tm, float *dst, int c0, int c1, unsigned long long *bar)
 {
-    const int main_px = min(128, nx - warp_x0);
-    const bool right = (warp_x0 + 128 < nx), left = (warp_x0 > 0);
-    const unsigned b_plain = 4u * (unsigned)(main_px + (right ? ST_PAD : 0));
-    const unsigned b_left = b_plain + (left ? 4u * ST_PAD : 0u);
-    mbar_expect_tx(bar, 8u * b_plain + 2u * b_left);
-    float *d = stage + ST_PAD;
-    const float *c = Q.c + delta, *u = Q.u + delta, *p = Q.p + delta;
-    bulk_g2s(d + 0 * ST_SLOT, u, b_plain, bar);                  // u1
-    bulk_g2s(d + 1 * ST_SLOT, u + Q.PL, b_plain, bar);           // u2
-    bulk_g2s(d + 2 * ST_SLOT, c, b_plain, bar);                  // gx
-    bulk_g2s(d + 3 * ST_SLOT, c + Q.PL, b_plain, bar);           // gy
-    bulk_g2s(d + 4 * ST_SLOT, c + 2 * Q.PL, b_plain, bar);       // g2
-    bulk_g2s(d + 5 * ST_SLOT, c + 3 * Q.PL, b_plain, bar);       // rc
-    bulk_g2s(d + 6 * ST_SLOT, p + Q.PL, b_plain, bar);           // p12
-    bulk_g2s(d + 7 * ST_SLOT, p + 3 * Q.PL, b_plain, bar);       // p22
-    const int lo = left ? ST_PAD : 0;    // p11 / p21 also need the pixel to the left of the warp's first
-    bulk_g2s(d + 8 * ST_SLOT - lo, p - lo, b_left, bar);         // p11
-    bulk_g2s(d + 9 * ST_SLOT - lo, p + 2 * Q.PL - lo, b_left, bar);   // p21
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// elected lane: queue the three box copies of the image row `delta` floats below the strip's first row into `stage`.
+// Out-of-range coordinates (left of pixel 0 of the plane, beyond its end) are zero-filled by the TMA unit and still
+// count towards the transaction bytes, so the byte count is a constant.
+__device__ __forceinline__ void tma_issue_row(const SolverArgs &A, const TmaSrc &Q, int delta, const TmaRing &T, unsigned n)
+{
+    float *stage = T.stage(n % ST_STAGES);
+    unsigned long long *bar = T.bar(n % ST_STAGES);
+    mbar_expect_tx(bar, 10u * ST_SLOT * 4u);
+    tma_box(&A.tm4, stage + ST_OFF_C, Q.c0 + delta, Q.row_c, bar);
+    tma_box(&A.tm2, stage + ST_OFF_U, Q.c0 + delta, Q.row_u, bar);
+    tma_box(&A.tm4, stage + ST_OFF_P, Q.c0 + delta, Q.row_p, bar);
 }
 
 // all lanes: wait for stage `st`, then evaluate the staged row straight out of shared memory.  The row is consumed in
 // two halves (dual variable -> divergence, then flow + constants -> primal update) so that at most half of its 52
 // input values are live in registers at any time.
-template <int st>
 __device__ __forceinline__ void tma_eval_row(TmaRing &T, int lane, const LaneEdges &E, bool first, bool last,
                                              const IterConsts &K, const float (&up12)[5], const float (&up22)[5],
                                              RowState<4> &R, int *status)
 {
-    const unsigned parity = T.uses[st] & 1u;
-    bool ok = mbar_try_wait(T.bar[st], parity);
+    const unsigned st = T.taken % ST_STAGES, parity = (T.taken / ST_STAGES) & 1u;
+    T.taken++;
+    unsigned long long *bar = T.bar(st);
+    bool ok = mbar_try_wait(bar, parity);
     for (unsigned spins = 0; !ok; ++spins) {
-        ok = mbar_try_wait(T.bar[st], parity);
+        ok = mbar_try_wait(bar, parity);
         if (!ok && spins > (1u << 22)) {            // ~ seconds: something is badly wrong, do not hang the GPU
             atomicExch(status, 2);
             break;
         }
     }
-    T.uses[st]++;
-    const float *s = T.stage[st] + ST_PAD + 4 * lane;
+    const float *s = T.stage(st) + ST_PAD + 4 * lane;
     RowIn<4> I;
     float4 v;
-#define TAKE(k, dst)                                                \
-    v = *reinterpret_cast<const float4 *>(s + (k) * ST_SLOT);       \
+#define TAKE(o, dst)                                                \
+    v = *reinterpret_cast<const float4 *>(s + (o));                 \
     I.dst[0] = v.x; I.dst[1] = v.y; I.dst[2] = v.z; I.dst[3] = v.w; \
-    I.dst[4] = E.right ? s[(k) * ST_SLOT + 4] : 0.f;
-    TAKE(6, p12) TAKE(7, p22) TAKE(8, a11) TAKE(9, a21)
-    I.l11 = E.left ? 0.f : s[8 * ST_SLOT - 1];
-    I.l21 = E.left ? 0.f : s[9 * ST_SLOT - 1];
+    I.dst[4] = E.right ? s[(o) + 4] : 0.f;
+    TAKE(ST_OFF_P + 1 * ST_SLOT, p12) TAKE(ST_OFF_P + 3 * ST_SLOT, p22) TAKE(ST_OFF_P, a11) TAKE(ST_OFF_P + 2 * ST_SLOT, a21)
+    I.l11 = E.left ? 0.f : s[ST_OFF_P - 1];
+    I.l21 = E.left ? 0.f : s[ST_OFF_P + 2 * ST_SLOT - 1];
     float d1[5], d2[5];
     eval_div<4>(I, E, first, last, up12, up22, R, d1, d2);
     asm volatile("" ::: "memory");                  // keep the second half's shared-memory loads below this point
-    TAKE(0, u1) TAKE(1, u2) TAKE(2, gx) TAKE(3, gy) TAKE(4, g2) TAKE(5, rc)
+    TAKE(ST_OFF_U, u1) TAKE(ST_OFF_U + ST_SLOT, u2)
+    TAKE(ST_OFF_C, gx) TAKE(ST_OFF_C + ST_SLOT, gy) TAKE(ST_OFF_C + 2 * ST_SLOT, g2) TAKE(ST_OFF_C + 3 * ST_SLOT, rc)
 #undef TAKE
     eval_primal<4>(I, K, d1, d2, R);
 }
 
 // One warp's strip with staged rows (V = 4): same arithmetic as iterate_strip<4>, different data path.
-__device__ __forceinline__ double iterate_strip_tma(const IterPtrs &P, TmaRing &T, int lane, int warp_x0, int y0, int y1,
-                                                    int nx, int ny, const IterConsts &K, int *status)
+__device__ __forceinline__ double iterate_strip_tma(const SolverArgs &SA, int group, const IterPtrs &P, TmaRing &T, int lane,
+                                                    int warp_x0, int y0, int y1, int nx, int ny, const IterConsts &K,
+                                                    int *status)
 {
     const int x0 = warp_x0 + 4 * lane;
     const bool active = x0 < nx;
@@ -236,15 +245,20 @@ __device__ __forceinline__ double iterate_strip_tma(const IterPtrs &P, TmaRing &
     const int nr = yend - y0 + 1;
     const long long wrow = (long long)y0 * nx + warp_x0;
     TmaSrc Q;
-    Q.c = P.gx() + wrow; Q.u = P.u1() + wrow; Q.p = P.p11() + wrow; Q.PL = P.PL;
+    Q.c0 = (int)wrow - ST_PAD;
+    Q.row_c = group * 18 + 2; Q.row_u = group * 18 + 6 + 2 * P.uc; Q.row_p = group * 18 + 10 + 4 * P.pc;
     double err = 0.0;
 
+    // prologue: the first ST_STAGES rows of the strip go in flight at once
     __syncwarp();
+    const unsigned n0 = T.issued;                        // == T.taken: the ring is empty between strips
     if (elect_one()) {
         fence_proxy_async();                             // other CTAs' stores (generic proxy) -> our bulk reads
-        tma_issue_row(Q, 0, warp_x0, nx, T.stage[0], T.bar[0]);
-        if (nr > 1) tma_issue_row(Q, nx, warp_x0, nx, T.stage[1], T.bar[1]);
+#pragma unroll
+        for (int k = 0; k < ST_STAGES; k++)
+            if (k < nr) tma_issue_row(SA, Q, k * nx, T, n0 + k);
     }
+    T.issued = n0 + (unsigned)min(nr, ST_STAGES);
     float up12[5], up22[5];
     long long row = (long long)y0 * nx + x0;
     if (active) {
@@ -254,27 +268,33 @@ __device__ __forceinline__ double iterate_strip_tma(const IterPtrs &P, TmaRing &
         for (int j = 0; j < 5; j++) up12[j] = up22[j] = 0.f;
     }
 
+    // after a row has been consumed its stage is refilled with the row ST_STAGES further down
+    auto refill = [&](int consumed) {
+        __syncwarp();                                    // every lane has pulled its values out of the stage
+        if (consumed + ST_STAGES < nr) {
+            if (elect_one()) tma_issue_row(SA, Q, (consumed + ST_STAGES) * nx, T, T.issued);
+            T.issued++;
+        }
+    };
+
     RowState<4> A, B;
-    tma_eval_row<0>(T, lane, E, y0 == 0, y0 == ny - 1, K, up12, up22, A, status);
-    __syncwarp();
-    if (nr > 2 && elect_one()) tma_issue_row(Q, 2LL * nx, warp_x0, nx, T.stage[0], T.bar[0]);
+    tma_eval_row(T, lane, E, y0 == 0, y0 == ny - 1, K, up12, up22, A, status);
+    refill(0);
 
     int y = y0, i = 0;                                   // i = y - y0
     while (true) {
         bool down = (i + 1 < nr);
-        if (down) {                                      // i is even here: row i+1 sits in stage 1
-            tma_eval_row<1>(T, lane, E, false, y + 2 == ny, K, A.p12, A.p22, B, status);
-            __syncwarp();
-            if (i + 3 < nr && elect_one()) tma_issue_row(Q, (long long)(i + 3) * nx, warp_x0, nx, T.stage[1], T.bar[1]);
+        if (down) {
+            tma_eval_row(T, lane, E, false, y + 2 == ny, K, A.p12, A.p22, B, status);
+            refill(i + 1);
         }
         finish_row<4>(P, row, E, down, K, A, B, err, active);
         row += nx; ++i;
         if (++y >= y1) break;
         down = (i + 1 < nr);
-        if (down) {                                      // i is odd here: row i+1 sits in stage 0
-            tma_eval_row<0>(T, lane, E, false, y + 2 == ny, K, B.p12, B.p22, A, status);
-            __syncwarp();
-            if (i + 3 < nr && elect_one()) tma_issue_row(Q, (long long)(i + 3) * nx, warp_x0, nx, T.stage[0], T.bar[0]);
+        if (down) {
+            tma_eval_row(T, lane, E, false, y + 2 == ny, K, B.p12, B.p22, A, status);
+            refill(i + 1);
         }
         finish_row<4>(P, row, E, down, K, B, A, err, active);
         row += nx; ++i;
@@ -286,8 +306,8 @@ __device__ __forceinline__ double iterate_strip_tma(const IterPtrs &P, TmaRing &
 // Distribute the image over the group's warps: column segments of 32*V pixels, strips of `rows` rows
 // (iterate_strip, the direct-load version, is in solver_core.h and shared with the host-compiled unit tests).
 template <int V>
-__device__ __forceinline__ double iterate_group(const IterPtrs &P, TmaRing &T, int nx, int ny, const IterConsts &K,
-                                                int gwarp, int nwarps_group, int *status)
+__device__ __forceinline__ double iterate_group(const SolverArgs &A, int group, const IterPtrs &P, TmaRing &T, int nx, int ny,
+                                                const IterConsts &K, int gwarp, int nwarps_group, int *status)
 {
     const int lane = threadIdx.x & 31;
     const StripPlan sp = plan_strips<V>(nx, ny, nwarps_group);
@@ -299,7 +319,7 @@ __device__ __forceinline__ double iterate_group(const IterPtrs &P, TmaRing &T, i
         const int y0 = strip * rows;
         const int y1 = min(ny, y0 + rows);
         if (V == 4) {
-            err += iterate_strip_tma(P, T, lane, col * segw, y0, y1, nx, ny, K, status);
+            err += iterate_strip_tma(A, group, P, T, lane, col * segw, y0, y1, nx, ny, K, status);
         } else {
             if (x0 < nx) err += iterate_strip<V>(P, x0, col * segw, y0, y1, nx, ny, K);
         }
@@ -309,7 +329,7 @@ __device__ __forceinline__ double iterate_group(const IterPtrs &P, TmaRing &T, i
 
 // ------------------------------------------------------------------------------------------------ the kernel
 
-__global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel(const SolverArgs A)
+__global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel(const __grid_constant__ SolverArgs A)
 {
     __shared__ double s_red[SOLVER_WARPS];
     __shared__ double s_val;
@@ -319,14 +339,11 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
     // per-warp staging ring for the bulk-copy row pipeline
     TmaRing T;
     {
-        unsigned char *base = s_dyn + (size_t)(threadIdx.x >> 5) * ST_WARP_BYTES;
+        T.base = s_dyn + (size_t)(threadIdx.x >> 5) * ST_WARP_BYTES;
+        T.issued = T.taken = 0u;
 #pragma unroll
-        for (int k = 0; k < ST_STAGES; k++) {
-            T.stage[k] = reinterpret_cast<float *>(base + (size_t)k * ST_ROW * 4);
-            T.bar[k] = reinterpret_cast<unsigned long long *>(base + (size_t)ST_STAGES * ST_ROW * 4 + 16 * k);
-            T.uses[k] = 0u;
-            if ((threadIdx.x & 31) == 0) mbar_init(T.bar[k], 1u);
-        }
+        for (int k = 0; k < ST_STAGES; k++)
+            if ((threadIdx.x & 31) == 0) mbar_init(T.bar(k), 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncthreads();
     }
@@ -403,8 +420,8 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
                         it++;
                         IterPtrs P;
                         P.S = S; P.PL = PL; P.uc = uc; P.pc = pc;
-                        double e = ((nx & 3) == 0) ? iterate_group<4>(P, T, nx, ny, K, gwarp, gwarps, A.status)
-                                                   : iterate_group<1>(P, T, nx, ny, K, gwarp, gwarps, A.status);
+                        double e = ((nx & 3) == 0) ? iterate_group<4>(A, group, P, T, nx, ny, K, gwarp, gwarps, A.status)
+                                                   : iterate_group<1>(A, group, P, T, nx, ny, K, gwarp, gwarps, A.status);
                         // CTA partial in a fixed order, then the group reduction rides on the barrier
                         for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
                         if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = e;

@@ -90,17 +90,91 @@ def precompute_video(frame_paths, flow_dir, warp_dir=None, patch_depth=2, future
     return written
 
 
+class _PipelinedGPU:
+    """Feeds batches to libBridge.so through its two staging slots (rvdd_flow_and_warp_host_submit / _wait): while
+    one batch is on the GPU the previous one is written to disk and the next one is read and uploaded."""
+
+    def __init__(self):
+        import torch
+        from . import bridge
+        self.torch, self.br = torch, bridge.default_bridge()
+        self.jobs = [None, None]
+        self.k = 0
+        self.written = []
+
+    def _buffers(self, slot, nfr, h, w, c, npairs, want_warp):
+        t = self.torch
+        key = (nfr, h, w, c, npairs, want_warp)
+        cache = getattr(self, "_cache", None) or {}
+        self._cache = cache
+        if (slot, key) not in cache:
+            cache[(slot, key)] = (t.empty((nfr, h, w, c), dtype=t.float32).pin_memory(),
+                                  t.empty((npairs, h, w, 2), dtype=t.float32).pin_memory(),
+                                  t.empty((npairs, h, w, c), dtype=t.float32).pin_memory() if want_warp else None)
+        return cache[(slot, key)]
+
+    def _finish(self, slot):
+        job = self.jobs[slot]
+        if job is None:
+            return
+        self.br.wait_host(slot)
+        batch, flow, warped = job
+        for k, p in enumerate(batch):
+            if not os.path.isfile(p["flow_file"]):
+                flowio.write_tif(p["flow_file"], flow[k].numpy())
+                self.written.append(p["flow_file"])
+            if p["warp_file"] and not os.path.isfile(p["warp_file"]):
+                flowio.write_tif(p["warp_file"], warped[k].numpy())
+                self.written.append(p["warp_file"])
+        self.jobs[slot] = None
+
+    def submit(self, frame_paths, batch, want_warp):
+        slot = self.k & 1
+        self.k += 1
+        self._finish(slot)                                  # this slot's previous batch: wait + write its files
+        used = sorted({p["src"] for p in batch} | {p["tgt"] for p in batch})
+        local = {f: i for i, f in enumerate(used)}
+        first = flowio.read_image(frame_paths[used[0]]).astype(np.float32)
+        h, w, c = first.shape
+        frames, flow, warped = self._buffers(slot, len(used), h, w, c, len(batch), want_warp)
+        frames[0].copy_(self.torch.from_numpy(first))
+        for i, f in enumerate(used[1:], 1):
+            frames[i].copy_(self.torch.from_numpy(flowio.read_image(frame_paths[f]).astype(np.float32)))
+        self.br.submit_host(slot, frames, [local[p["src"]] for p in batch], [local[p["tgt"]] for p in batch], flow, warped)
+        self.jobs[slot] = (batch, flow, warped)
+
+    def drain(self):
+        self._finish(0)
+        self._finish(1)
+        return self.written
+
+
 def precompute_dataset(videos, flow_root, warp_root=None, patch_depth=2, future_patch_depth=0, rank=0, world=1,
-                       compute=gpu_compute, gather=None):
+                       compute=None, gather=None, max_pairs_per_batch=64):
     """``videos``: list of (name, [frame paths]).  Rank ``rank`` of ``world`` handles its round-robin shard.
 
+    With ``compute=None`` the batches go through the GPU pipeline (upload / solve / download + file writing overlap
+    across batches); an injected ``compute(frames, src, tgt, want_warp)`` is called synchronously per batch.
     ``gather`` (optional) receives this rank's list of written files and returns the lists of all ranks -- with
     torch.distributed that is ``all_gather_object``; it is the only communication of the whole job."""
     mine = shard(videos, rank, world)
     written = []
+    pipe = _PipelinedGPU() if compute is None else None
     for name, paths in mine:
-        written += precompute_video(paths, os.path.join(flow_root, name), os.path.join(warp_root, name) if warp_root else None,
-                                    patch_depth, future_patch_depth, compute)
+        flow_dir = os.path.join(flow_root, name)
+        warp_dir = os.path.join(warp_root, name) if warp_root else None
+        if pipe is None:
+            written += precompute_video(paths, flow_dir, warp_dir, patch_depth, future_patch_depth, compute, max_pairs_per_batch)
+            continue
+        todo = plan_video(paths, flow_dir, warp_dir, patch_depth, future_patch_depth)
+        if todo:
+            os.makedirs(flow_dir, exist_ok=True)
+            if warp_dir:
+                os.makedirs(warp_dir, exist_ok=True)
+        for b0 in range(0, len(todo), max_pairs_per_batch):
+            pipe.submit(paths, todo[b0:b0 + max_pairs_per_batch], warp_dir is not None)
+    if pipe is not None:
+        written += pipe.drain()
     if gather is not None:
         return [f for part in gather(written) for f in part]
     return written

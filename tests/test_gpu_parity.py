@@ -296,3 +296,27 @@ def test_pipelined_host_submissions(bridge, port):
         assert torch.equal(flows[k], want[k][0]) and torch.equal(warps[k], want[k][1])
     g = np.mean(seqs[1].numpy(), axis=3)
     assert np.array_equal(flows[1][0].numpy().transpose(2, 0, 1), port.tvl1flow(g[1], g[0]))
+
+
+def test_precompute_driver_on_gpu(tmp_path, bridge, port):
+    """The offline flow cache end to end on the GPU: frame TIFFs in, <from>_<to>.tif flows out (pipelined batches),
+    identical to what the reference's createWarpedInputData would write (base_dataset.py:134-191)."""
+    from rvdd_release_b200 import flowio, precompute
+    videos = []
+    for v, iso in enumerate(("iso3200", "iso12800", "clean")):
+        d = tmp_path / "noisy" / ("seq%d" % v)
+        d.mkdir(parents=True)
+        seq = synth.sequence(4, 48, 80, iso, noise_seed=11 * v).numpy()
+        for f in range(4):
+            flowio.write_tif(str(d / ("%03d.tif" % f)), seq[f])
+        videos.append((seq, str(d)))
+    listed = precompute.list_videos(str(tmp_path / "noisy"))
+    files = precompute.precompute_dataset(listed, str(tmp_path / "flow"), None, 2, 1, max_pairs_per_batch=4)
+    assert len(files) == 3 * 6
+    for v, (seq, _) in enumerate(videos):
+        g = np.mean(seq, axis=3)
+        past = flowio.read_tif(str(tmp_path / "flow" / ("seq%d" % v) / "001_002.tif"))        # source 001 -> target 002
+        assert np.array_equal(past.transpose(2, 0, 1), port.tvl1flow(g[2], g[1]))
+        fut = flowio.read_tif(str(tmp_path / "flow" / ("seq%d" % v) / "003_002.tif"))         # future source 003 -> target 002
+        assert np.array_equal(fut.transpose(2, 0, 1), port.tvl1flow(g[2], g[3]))
+    assert precompute.precompute_dataset(listed, str(tmp_path / "flow"), None, 2, 1) == []    # resume: nothing to do

@@ -237,6 +237,7 @@ def run_ours(args, rank, local_rank, world):
     ms = e0.elapsed_time(e1)
     solver_ms = br.profile_read()
     scale_ms = br.profile_scales()
+    phase_ms = br.profile_phases()
     br.profile(False)
     br.check(dev)
     if world > 1:
@@ -325,6 +326,8 @@ def run_ours(args, rank, local_rank, world):
         "cpu_baseline": cpu,
         "iterations_per_scale_mean": iters.sum(axis=2).mean(axis=0).tolist(),
         "ms_per_pair_at_scale": scale_ms,
+        "ms_per_pair_warp_constants_at_scale": [round(a, 4) for a, _ in phase_ms],
+        "ms_per_pair_iterations_at_scale": [round(b, 4) for _, b in phase_ms],
         "pixel_iterations_per_pair": float(sum(nx * ny * iters[:, s].sum() for s, (nx, ny) in enumerate(sizes)) / npairs),
         "flow_checksum": checksum,
     }))

@@ -101,6 +101,9 @@ RVDD_API int rvdd_profile_read(rvdd_ctx *ctx, float *solver_ms, int cap);
 /* With profiling enabled the solver also stamps %globaltimer when a pair enters each pyramid level; this returns the
  * mean time (ms) a pair of the last launch spent at level s in ms[s] (0 = finest).  Returns the number of levels. */
 RVDD_API int rvdd_profile_scales(rvdd_ctx *ctx, float *ms, int cap);
+/* Same launch split by phase: ms[2*s] = warp-constants phases of level s (tvl1flow_lib.c:143-159), ms[2*s+1] = its
+ * iteration loops (:161-244).  Returns the number of levels, negative on error. */
+RVDD_API int rvdd_profile_phases(rvdd_ctx *ctx, float *ms, int cap);
 
 /* Test hook: run `blocks` x 256 threads x `iters` pseudo-random trials of the kernels' straight-line exact
  * division / hypot fast paths against IEEE division and the double-precision square root on the device.

@@ -43,6 +43,7 @@ _SIGNATURES = {
     "rvdd_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "rvdd_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
     "rvdd_profile_scales": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
+    "rvdd_profile_phases": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
     "rvdd_selftest_fastmath": (C.c_int, [C.c_ulonglong, C.c_int, C.c_int, C.POINTER(C.c_ulonglong)]),
     "rvdd_debug_level_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "rvdd_warp_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -176,6 +177,12 @@ class Bridge:
         buf = (C.c_float * TRACE_SCALES)()
         n = self.lib.rvdd_profile_scales(self.ctx, buf, TRACE_SCALES)
         return [buf[i] for i in range(max(n, 0))]
+
+    def profile_phases(self):
+        """-> [(ms in the warp-constants phases, ms in the iteration loops)] per pyramid level of the last profiled launch."""
+        buf = (C.c_float * (2 * TRACE_SCALES))()
+        n = self.lib.rvdd_profile_phases(self.ctx, buf, 2 * TRACE_SCALES)
+        return [(buf[2 * i], buf[2 * i + 1]) for i in range(max(n, 0))]
 
     def debug_level(self, pair, which, level, nx, ny):
         """Pyramid level of the last tvl1_flow call (test hook, rvdd_debug_level_dev)."""

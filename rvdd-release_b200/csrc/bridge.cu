@@ -305,7 +305,7 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
     if (G > total_ctas) G = total_ctas;
     const int C = total_ctas / G;
     const long long plane = ((long long)nx * ny + 3) & ~3LL;
-    const long long scratch_stride = 18 * plane;
+    const long long scratch_stride = RVDD_NPLANES * plane;
     CK(c->pyr.ensure(sizeof(float) * (size_t)(2 * K) * P.total));
     CK(c->tmp.ensure(sizeof(float) * (size_t)(2 * K) * plane));
     CK(c->scratch.ensure(sizeof(float) * (size_t)G * scratch_stride));
@@ -376,12 +376,14 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
     A.pyr0 = pyr; A.pyr1 = pyr + (long long)K * P.total; A.pyr_stride = P.total;
     A.flow_out = flow;
     A.scratch = (float *)c->scratch.p; A.scratch_stride = scratch_stride; A.plane = plane;
-    if (encode_scratch_map(&A.tm4, A.scratch, plane, 18LL * G, 4)) return -1;
-    if (encode_scratch_map(&A.tm2, A.scratch, plane, 18LL * G, 2)) return -1;
+    if (encode_scratch_map(&A.tm4, A.scratch, plane, (long long)RVDD_NPLANES * G, 4)) return -1;
+    if (encode_scratch_map(&A.tm3, A.scratch, plane, (long long)RVDD_NPLANES * G, 3)) return -1;
+    if (encode_scratch_map(&A.tm2, A.scratch, plane, (long long)RVDD_NPLANES * G, 2)) return -1;
     A.iters_out = iters; A.err_out = nullptr;
     A.scale_ns = nullptr;
     if (c->prof) {
-        CK(c->stamps.ensure(sizeof(unsigned long long) * (size_t)K * (RVDD_MAX_SCALES + 1)));
+        CK(c->stamps.ensure(sizeof(unsigned long long) * (size_t)K * (RVDD_MAX_SCALES + 1 + 2 * RVDD_MAX_SCALES)));
+        CK(cudaMemsetAsync(c->stamps.p, 0, sizeof(unsigned long long) * (size_t)K * (RVDD_MAX_SCALES + 1 + 2 * RVDD_MAX_SCALES), st));
         A.scale_ns = (unsigned long long *)c->stamps.p;
     }
     A.bar = bar; A.partials = partials; A.status = status;
@@ -432,6 +434,26 @@ extern "C" int rvdd_profile_scales(rvdd_ctx *c, float *ms, int cap)
         ms[s] = (float)(acc / K);
     }
     return S < cap ? S : cap;
+}
+
+// Same launch, split by phase: ms[2 * s] = time a pair spent in the warp-constants phases of level s (bicubic warps of
+// I1 and its gradient, tvl1flow_lib.c:143-159), ms[2 * s + 1] = in its primal-dual iteration loops (:161-244).
+extern "C" int rvdd_profile_phases(rvdd_ctx *c, float *ms, int cap)
+{
+    if (!c || !c->stamps.p || c->last_pairs <= 0) return -1;
+    const int K = c->last_pairs, S = c->last_pyr.S;
+    std::vector<unsigned long long> h((size_t)K * 2 * RVDD_MAX_SCALES);
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpy(h.data(), (const unsigned long long *)c->stamps.p + (size_t)K * (RVDD_MAX_SCALES + 1),
+                   sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return -1;
+    for (int s = 0; s < S && 2 * s + 1 < cap; s++)
+        for (int ph = 0; ph < 2; ph++) {
+            double acc = 0;
+            for (int k = 0; k < K; k++) acc += (double)h[((size_t)k * RVDD_MAX_SCALES + s) * 2 + ph] * 1e-6;
+            ms[2 * s + ph] = (float)(acc / K);
+        }
+    return S;
 }
 
 extern "C" int rvdd_profile_read(rvdd_ctx *c, float *solver_ms, int cap)

@@ -23,9 +23,11 @@ struct GaussTaps {
 
 // Arguments of the persistent solver kernel (solver.cu).
 struct SolverArgs {
-    // TMA descriptors of the whole solver scratch viewed as a 2-D tensor [ngroups * 18 planes][plane floats]; the
-    // boxes are one staged row segment (136 floats) of 4 adjacent planes (constants, dual variable) or 2 (flow).
+    // TMA descriptors of the whole solver scratch viewed as a 2-D tensor [ngroups * RVDD_NPLANES planes][plane
+    // floats]; the boxes are one staged row segment (136 floats) of 4 adjacent planes (dual variable), 3 (per-warp
+    // constants) or 2 (flow).
     alignas(64) CUtensorMap tm4;
+    alignas(64) CUtensorMap tm3;
     alignas(64) CUtensorMap tm2;
     int npairs, S, fscale, nwarps;
     int nx[RVDD_MAX_SCALES], ny[RVDD_MAX_SCALES];

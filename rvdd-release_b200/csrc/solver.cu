@@ -10,7 +10,8 @@
 // reference's stopping rule `while (error > eps^2 && n < 300)` (tvl1flow_lib.c:163) is evaluated on the device
 // after EVERY iteration, identically by every CTA of the group -- no host round trip, no speculation.
 //
-// One iteration is a single pass (64 B/pixel of HBM traffic: read u, p, the four per-warp constants, write u, p):
+// One iteration is a single pass (60 B/pixel of HBM traffic: read u, p and three per-warp constants, write u, p; the
+// reference's fourth per-warp array, |grad|^2, is recomputed from I1wx, I1wy instead of being stored):
 // each warp marches down a strip of rows, 4 pixels per lane; the thresholding step + primal update of the row
 // below (needed by the forward differences of the dual update) is computed once and carried in registers to
 // the next step, so only the strip's last row is evaluated twice.  u and p are double-buffered (read A, write B).
@@ -97,6 +98,9 @@ __device__ __forceinline__ double group_sum(const GroupCtx &g, int slot, double 
 #ifndef SOLVER_V
 #define SOLVER_V 4
 #endif
+#ifndef WC_BATCH
+#define WC_BATCH 2                       // pixels per thread and trip of the warp-constants phase (loads in flight)
+#endif
 
 // ---- bulk-copy (TMA) row staging, used when the image width is a multiple of 4 ---------------------------------
 //
@@ -104,18 +108,18 @@ __device__ __forceinline__ double group_sum(const GroupCtx &g, int slot, double 
 // it, computes, and only then asks for the next; with 16 warps per SM (the state of a 4-pixel lane needs ~128
 // registers) that is ~30 KB in flight per SM, good for ~2.5 TB/s.  So every warp stages the rows it is about to
 // process in shared memory with 1-D bulk asynchronous copies (cp.async.bulk global -> shared, completion on an
-// mbarrier): 10 arrays x (128 pixels + a 4-pixel block on either side) per row, two rows per warp in flight.  The
+// mbarrier): 9 arrays x (128 pixels + a 4-pixel block on either side) per row, two rows per warp in flight.  The
 // copy of row y+3 is issued as soon as row y+1 has been consumed, so the loads of the next rows overlap the
 // arithmetic of the current one.  The right/left neighbour pixels come out of the same staged row.
 
 #define ST_PAD 4                         // pixels staged on either side of the warp's 128
 #define ST_SLOT (128 + 2 * ST_PAD)       // floats per array per row (544 B, a multiple of 16 B)
 // One staged row = three TMA boxes, each landing at a 128-byte aligned offset of the stage:
-//   [gx gy g2 rc] (4 planes) at float 0, [u1 u2] at float 544, [p11 p12 p21 p22] at float 832
+//   [gx gy rc] (3 planes) at float 0, [u1 u2] at float 416, [p11 p12 p21 p22] at float 704
 #define ST_OFF_C 0
-#define ST_OFF_U (4 * ST_SLOT)
-#define ST_OFF_P 832
-#define ST_ROW 1408                      // floats per stage (5632 B, a multiple of 128 B)
+#define ST_OFF_U 416
+#define ST_OFF_P 704
+#define ST_ROW 1248                      // floats per stage (4992 B, a multiple of 128 B)
 #ifndef ST_STAGES
 #define ST_STAGES 2
 #endif
@@ -170,7 +174,7 @@ __device__ __forceinline__ bool elect_one()
 }
 
 // Row coordinates of a strip for the tensor-map copies: c0 = linear float index of (y, warp_x0 - ST_PAD) inside a plane,
-// plane rows of the three families in the [ngroups * 18][plane] view of the scratch.
+// plane rows of the three families in the [ngroups * RVDD_NPLANES][plane] view of the scratch.
 struct TmaSrc {
     int c0, row_c, row_u, row_p;
 };
@@ -190,14 +194,14 @@ __device__ __forceinline__ void tma_issue_row(const SolverArgs &A, const TmaSrc 
 {
     float *stage = T.stage(n % ST_STAGES);
     unsigned long long *bar = T.bar(n % ST_STAGES);
-    mbar_expect_tx(bar, 10u * ST_SLOT * 4u);
-    tma_box(&A.tm4, stage + ST_OFF_C, Q.c0 + delta, Q.row_c, bar);
+    mbar_expect_tx(bar, 9u * ST_SLOT * 4u);
+    tma_box(&A.tm3, stage + ST_OFF_C, Q.c0 + delta, Q.row_c, bar);
     tma_box(&A.tm2, stage + ST_OFF_U, Q.c0 + delta, Q.row_u, bar);
     tma_box(&A.tm4, stage + ST_OFF_P, Q.c0 + delta, Q.row_p, bar);
 }
 
 // all lanes: wait for stage `st`, then evaluate the staged row straight out of shared memory.  The row is consumed in
-// two halves (dual variable -> divergence, then flow + constants -> primal update) so that at most half of its 52
+// two halves (dual variable -> divergence, then flow + constants -> primal update) so that at most half of its 47
 // input values are live in registers at any time.
 __device__ __forceinline__ void tma_eval_row(TmaRing &T, int lane, const LaneEdges &E, bool first, bool last,
                                              const IterConsts &K, const float (&up12)[5], const float (&up22)[5],
@@ -228,7 +232,7 @@ __device__ __forceinline__ void tma_eval_row(TmaRing &T, int lane, const LaneEdg
     eval_div<4>(I, E, first, last, up12, up22, R, d1, d2);
     asm volatile("" ::: "memory");                  // keep the second half's shared-memory loads below this point
     TAKE(ST_OFF_U, u1) TAKE(ST_OFF_U + ST_SLOT, u2)
-    TAKE(ST_OFF_C, gx) TAKE(ST_OFF_C + ST_SLOT, gy) TAKE(ST_OFF_C + 2 * ST_SLOT, g2) TAKE(ST_OFF_C + 3 * ST_SLOT, rc)
+    TAKE(ST_OFF_C, gx) TAKE(ST_OFF_C + ST_SLOT, gy) TAKE(ST_OFF_C + 2 * ST_SLOT, rc)
 #undef TAKE
     eval_primal<4>(I, K, d1, d2, R);
 }
@@ -246,7 +250,8 @@ __device__ __forceinline__ double iterate_strip_tma(const SolverArgs &SA, int gr
     const long long wrow = (long long)y0 * nx + warp_x0;
     TmaSrc Q;
     Q.c0 = (int)wrow - ST_PAD;
-    Q.row_c = group * 18 + 2; Q.row_u = group * 18 + 6 + 2 * P.uc; Q.row_p = group * 18 + 10 + 4 * P.pc;
+    Q.row_c = group * RVDD_NPLANES + RVDD_PL_C; Q.row_u = group * RVDD_NPLANES + RVDD_PL_U + 2 * P.uc;
+    Q.row_p = group * RVDD_NPLANES + RVDD_PL_P + 4 * P.pc;
     double err = 0.0;
 
     // prologue: the first ST_STAGES rows of the strip go in flight at once
@@ -327,6 +332,60 @@ __device__ __forceinline__ double iterate_group(const SolverArgs &A, int group, 
     return err;
 }
 
+// ------------------------------------------------------------------------------------------------ warp constants
+
+// The per-warp constants of a whole level (tvl1flow_lib.c:143-159).  The image is cut into tiles of 32 columns x TR
+// rows; a warp marches down its tile WC_BATCH rows at a time, so three of the four tap rows of every bicubic window
+// were touched by the same warp one trip earlier and come out of L1, and the flow / I0 values of the next trip are
+// requested before the double-precision arithmetic of the current one starts.
+__device__ __forceinline__ void warp_consts_group(const float *I0, const float *I1, const float *I1x, const float *I1y,
+                                                  const float *u1, const float *u2, float *gx, float *gy, float *rc, int nx,
+                                                  int ny, int gwarp, int gwarps)
+{
+    const int lane = threadIdx.x & 31;
+    const int ncolt = (nx + 31) >> 5;
+    // tile height: the candidate in [16, 32] that needs the fewest row-trips per warp; small levels get one tile per warp
+    int TR = ((ny * ncolt + gwarps - 1) / gwarps + WC_BATCH - 1) / WC_BATCH * WC_BATCH;
+    if (TR > 16) {
+        int best = 1 << 30;
+        for (int c = 16; c <= 32; c += WC_BATCH) {
+            const int tiles = ncolt * ((ny + c - 1) / c), cost = ((tiles + gwarps - 1) / gwarps) * c;
+            if (cost < best) { best = cost; TR = c; }
+        }
+    }
+    const int ntr = (ny + TR - 1) / TR, ntiles = ncolt * ntr;
+    for (int t = gwarp; t < ntiles; t += gwarps) {
+        const int tyi = t / ncolt, cx = t - tyi * ncolt;
+        const int x = cx * 32 + lane, y0 = tyi * TR, y1 = min(ny, y0 + TR);
+        const bool lane_on = x < nx;
+        float a[WC_BATCH], b[WC_BATCH], i0[WC_BATCH], na[WC_BATCH], nb[WC_BATCH], ni0[WC_BATCH];
+        int px[WC_BATCH], py[WC_BATCH];
+        bool act[WC_BATCH];
+#pragma unroll
+        for (int k = 0; k < WC_BATCH; k++) {
+            px[k] = x;
+            const bool on = lane_on && y0 + k < y1;
+            const long long i = on ? (long long)(y0 + k) * nx + x : 0;
+            na[k] = u1[i]; nb[k] = u2[i]; ni0[k] = I0[i];
+        }
+        for (int y = y0; y < y1; y += WC_BATCH) {
+#pragma unroll
+            for (int k = 0; k < WC_BATCH; k++) {
+                a[k] = na[k]; b[k] = nb[k]; i0[k] = ni0[k];
+                py[k] = y + k;
+                act[k] = lane_on && y + k < y1;
+            }
+#pragma unroll
+            for (int k = 0; k < WC_BATCH; k++) {          // next trip's inputs: in flight during this trip's arithmetic
+                const bool on = lane_on && y + WC_BATCH + k < y1;
+                const long long i = on ? (long long)(y + WC_BATCH + k) * nx + x : 0;
+                na[k] = u1[i]; nb[k] = u2[i]; ni0[k] = I0[i];
+            }
+            warp_consts_eval<WC_BATCH>(I1, I1x, I1y, a, b, i0, px, py, act, nx, ny, gx, gy, rc);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ the kernel
 
 __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel(const __grid_constant__ SolverArgs A)
@@ -367,13 +426,22 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
     // per-group scratch planes
     float *S = A.scratch + (long long)group * A.scratch_stride;
     const long long PL = A.plane;
-    float *I1x = S, *I1y = S + PL, *gx = S + 2 * PL, *gy = S + 3 * PL, *g2 = S + 4 * PL, *rc = S + 5 * PL;
-    // flow and dual variable are double-buffered: plane 6 + 2*buf + comp and 10 + 4*buf + comp (no pointer tables:
+    float *I1x = S, *I1y = S + PL, *gx = S + RVDD_PL_C * PL, *gy = S + (RVDD_PL_C + 1) * PL, *rc = S + (RVDD_PL_C + 2) * PL;
+    // flow and dual variable are double-buffered: plane 5 + 2*buf + comp and 9 + 4*buf + comp (no pointer tables:
     // indexing a local array of pointers would force generic loads and local memory)
-#define UB(buf, comp) (S + (6 + 2 * (buf) + (comp)) * PL)
-#define PB(buf, comp) (S + (10 + 4 * (buf) + (comp)) * PL)
+#define UB(buf, comp) (S + (RVDD_PL_U + 2 * (buf) + (comp)) * PL)
+#define PB(buf, comp) (S + (RVDD_PL_P + 4 * (buf) + (comp)) * PL)
     IterConsts K;
     K.l_t = A.l_t; K.theta = A.theta; K.taut = A.taut; K.g0f = A.g0f;
+
+    // profiling: the group's leader thread accumulates the time a pair spends in the warp-constants phases and in the
+    // iteration loops of every level (read back by rvdd_profile_phases)
+    const bool stamping = A.scale_ns && g.cta == 0 && threadIdx.x == 0;
+    auto now_ns = []() {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        return t;
+    };
 
     for (int pair = group; pair < A.npairs; pair += A.ngroups) {
         const float *P0 = A.pyr0 + (long long)pair * A.pyr_stride;
@@ -404,14 +472,14 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
                 }
                 if (!group_sync(g, &s_flag)) return;
 
+                unsigned long long ns_consts = 0ULL, ns_iter = 0ULL;
                 for (int w = 0; w < A.nwarps; w++) {
+                    const unsigned long long tp0 = stamping ? now_ns() : 0ULL;
                     // ---- warp constants (:143-159): bicubic samples of I1, I1x, I1y at x + u
                     const float *u1 = UB(uc, 0), *u2 = UB(uc, 1);
-                    for (int i = gtid; i < n; i += gthreads) {
-                        const int y = i / nx, x = i - y * nx;
-                        warp_consts_px(I0, I1, I1x, I1y, u1[i], u2[i], x, y, nx, ny, &gx[i], &gy[i], &g2[i], &rc[i]);
-                    }
+                    warp_consts_group(I0, I1, I1x, I1y, u1, u2, gx, gy, rc, nx, ny, gwarp, gwarps);
                     if (!group_sync(g, &s_flag)) return;
+                    const unsigned long long tp1 = stamping ? now_ns() : 0ULL;
 
                     // ---- inner loop (:161-244), stop test after every iteration
                     int it = 0;
@@ -443,6 +511,17 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
                         if (A.iters_out) A.iters_out[t] = it;
                         if (A.err_out) A.err_out[t] = err;
                     }
+                    if (stamping) {
+                        const unsigned long long tp2 = now_ns();
+                        ns_consts += tp1 - tp0;
+                        ns_iter += tp2 - tp1;
+                    }
+                }
+                if (stamping) {
+                    unsigned long long *ph = A.scale_ns + (long long)A.npairs * (RVDD_MAX_SCALES + 1) +
+                                             ((long long)pair * RVDD_MAX_SCALES + s) * 2;
+                    ph[0] = ns_consts;
+                    ph[1] = ns_iter;
                 }
             }
 

@@ -33,29 +33,31 @@ template <> struct Vec<1> {
     RVDD_HDM void st(float *p, const float (&v)[1]) { *p = v[0]; }
 };
 
-// All arrays of one iteration are planes of the group's scratch block: plane 2..5 = the per-warp constants, plane
-// 6 + 2*buf + c = flow component c of buffer buf, plane 10 + 4*buf + c = dual variable.  Buffer (uc, pc) is read,
-// the other one written.  Addresses are formed on demand from (S, PL) instead of keeping 16 pointers in registers.
+// All arrays of one iteration are planes of the group's scratch block: planes 0, 1 = centred gradient of I1, planes
+// 2..4 = the per-warp constants I1wx, I1wy, rho_c (|grad|^2 is NOT stored: the iteration recomputes it from I1wx, I1wy
+// with the reference's own three float operations, tvl1flow_lib.c:155, which is cheaper than reading 4 more bytes per
+// pixel per iteration), plane 5 + 2*buf + c = flow component c of buffer buf, plane 9 + 4*buf + c = dual variable.
+// Buffer (uc, pc) is read, the other one written.  Addresses are formed on demand from (S, PL) instead of keeping 15
+// pointers in registers.
 struct IterPtrs {
     float *S;
     long long PL;
     int uc, pc;
-    RVDD_HDX const float *gx() const { return S + 2 * PL; }
-    RVDD_HDX const float *gy() const { return S + 3 * PL; }
-    RVDD_HDX const float *g2() const { return S + 4 * PL; }
-    RVDD_HDX const float *rc() const { return S + 5 * PL; }
-    RVDD_HDX const float *u1() const { return S + (6 + 2 * uc) * PL; }
-    RVDD_HDX const float *u2() const { return S + (7 + 2 * uc) * PL; }
-    RVDD_HDX const float *p11() const { return S + (10 + 4 * pc) * PL; }
-    RVDD_HDX const float *p12() const { return S + (11 + 4 * pc) * PL; }
-    RVDD_HDX const float *p21() const { return S + (12 + 4 * pc) * PL; }
-    RVDD_HDX const float *p22() const { return S + (13 + 4 * pc) * PL; }
-    RVDD_HDX float *nu1() const { return S + (6 + 2 * (uc ^ 1)) * PL; }
-    RVDD_HDX float *nu2() const { return S + (7 + 2 * (uc ^ 1)) * PL; }
-    RVDD_HDX float *np11() const { return S + (10 + 4 * (pc ^ 1)) * PL; }
-    RVDD_HDX float *np12() const { return S + (11 + 4 * (pc ^ 1)) * PL; }
-    RVDD_HDX float *np21() const { return S + (12 + 4 * (pc ^ 1)) * PL; }
-    RVDD_HDX float *np22() const { return S + (13 + 4 * (pc ^ 1)) * PL; }
+    RVDD_HDX const float *gx() const { return S + RVDD_PL_C * PL; }
+    RVDD_HDX const float *gy() const { return S + (RVDD_PL_C + 1) * PL; }
+    RVDD_HDX const float *rc() const { return S + (RVDD_PL_C + 2) * PL; }
+    RVDD_HDX const float *u1() const { return S + (RVDD_PL_U + 2 * uc) * PL; }
+    RVDD_HDX const float *u2() const { return S + (RVDD_PL_U + 1 + 2 * uc) * PL; }
+    RVDD_HDX const float *p11() const { return S + (RVDD_PL_P + 4 * pc) * PL; }
+    RVDD_HDX const float *p12() const { return S + (RVDD_PL_P + 1 + 4 * pc) * PL; }
+    RVDD_HDX const float *p21() const { return S + (RVDD_PL_P + 2 + 4 * pc) * PL; }
+    RVDD_HDX const float *p22() const { return S + (RVDD_PL_P + 3 + 4 * pc) * PL; }
+    RVDD_HDX float *nu1() const { return S + (RVDD_PL_U + 2 * (uc ^ 1)) * PL; }
+    RVDD_HDX float *nu2() const { return S + (RVDD_PL_U + 1 + 2 * (uc ^ 1)) * PL; }
+    RVDD_HDX float *np11() const { return S + (RVDD_PL_P + 4 * (pc ^ 1)) * PL; }
+    RVDD_HDX float *np12() const { return S + (RVDD_PL_P + 1 + 4 * (pc ^ 1)) * PL; }
+    RVDD_HDX float *np21() const { return S + (RVDD_PL_P + 2 + 4 * (pc ^ 1)) * PL; }
+    RVDD_HDX float *np22() const { return S + (RVDD_PL_P + 3 + 4 * (pc ^ 1)) * PL; }
 };
 
 struct IterConsts {
@@ -94,7 +96,7 @@ template <int V> RVDD_HD LaneEdges lane_edges(int x0, int nx, int warp_x0)
 // The inputs of one row for one lane: V own pixels plus the right neighbour (index V) of the flow, the per-warp
 // constants and the dual variable, and the left neighbour of p11 / p21.
 template <int V> struct RowIn {
-    float u1[V + 1], u2[V + 1], gx[V + 1], gy[V + 1], g2[V + 1], rc[V + 1], a11[V + 1], a21[V + 1];
+    float u1[V + 1], u2[V + 1], gx[V + 1], gy[V + 1], rc[V + 1], a11[V + 1], a21[V + 1];
     float p12[V + 1], p22[V + 1];
     float l11, l21;
 };
@@ -115,9 +117,6 @@ template <int V> RVDD_HD void load_row_global(const IterPtrs &P, long long row, 
     Vec<V>::ld(P.gy() + row, t);
 #pragma unroll
     for (int j = 0; j < V; j++) I.gy[j] = t[j];
-    Vec<V>::ld(P.g2() + row, t);
-#pragma unroll
-    for (int j = 0; j < V; j++) I.g2[j] = t[j];
     Vec<V>::ld(P.rc() + row, t);
 #pragma unroll
     for (int j = 0; j < V; j++) I.rc[j] = t[j];
@@ -133,10 +132,10 @@ template <int V> RVDD_HD void load_row_global(const IterPtrs &P, long long row, 
     Vec<V>::ld(P.p22() + row, t);
 #pragma unroll
     for (int j = 0; j < V; j++) I.p22[j] = t[j];
-    I.u1[V] = I.u2[V] = I.gx[V] = I.gy[V] = I.g2[V] = I.rc[V] = I.a11[V] = I.a21[V] = I.p12[V] = I.p22[V] = 0.f;
+    I.u1[V] = I.u2[V] = I.gx[V] = I.gy[V] = I.rc[V] = I.a11[V] = I.a21[V] = I.p12[V] = I.p22[V] = 0.f;
     if (E.right) {
         const long long q = row + V;
-        I.u1[V] = P.u1()[q]; I.u2[V] = P.u2()[q]; I.gx[V] = P.gx()[q]; I.gy[V] = P.gy()[q]; I.g2[V] = P.g2()[q]; I.rc[V] = P.rc()[q];
+        I.u1[V] = P.u1()[q]; I.u2[V] = P.u2()[q]; I.gx[V] = P.gx()[q]; I.gy[V] = P.gy()[q]; I.rc[V] = P.rc()[q];
         I.a11[V] = P.p11()[q]; I.a21[V] = P.p21()[q]; I.p12[V] = P.p12()[q]; I.p22[V] = P.p22()[q];
     }
     I.l11 = I.l21 = 0.f;
@@ -186,7 +185,8 @@ RVDD_HD void eval_div(const RowIn<V> &I, const LaneEdges &E, bool first, bool la
     }
 }
 
-// Part 2 needs the flow and the per-warp constants (u1, u2, gx, gy, g2, rc): thresholding + primal update + residual.
+// Part 2 needs the flow and the per-warp constants (u1, u2, gx, gy, rc): thresholding + primal update + residual.
+// grad = I1wx^2 + I1wy^2 (tvl1flow_lib.c:155) is formed here from the same two floats the reference squares.
 template <int V>
 RVDD_HD void eval_primal(const RowIn<V> &I, const IterConsts &K, const float (&d1)[V + 1], const float (&d2)[V + 1],
                          RowState<V> &R)
@@ -195,12 +195,12 @@ RVDD_HD void eval_primal(const RowIn<V> &I, const IterConsts &K, const float (&d
     bool bad = false;
 #pragma unroll
     for (int j = 0; j <= V; j++)
-        rvdd_primal_px_fast(I.u1[j], I.u2[j], I.gx[j], I.gy[j], I.g2[j], I.rc[j], d1[j], d2[j], K.l_t, K.theta, K.g0f,
+        rvdd_primal_px_fast(I.u1[j], I.u2[j], I.gx[j], I.gy[j], rvdd_grad2(I.gx[j], I.gy[j]), I.rc[j], d1[j], d2[j], K.l_t, K.theta, K.g0f,
                             &R.n1[j], &R.n2[j], bad);
     if (bad) {      // rare: some quotient could not be proven exact -> the reference-exact routine for this row
 #pragma unroll
         for (int j = 0; j <= V; j++) {
-            const float2 n = rvdd_primal_px_slow(I.u1[j], I.u2[j], I.gx[j], I.gy[j], I.g2[j], I.rc[j], d1[j], d2[j],
+            const float2 n = rvdd_primal_px_slow(I.u1[j], I.u2[j], I.gx[j], I.gy[j], rvdd_grad2(I.gx[j], I.gy[j]), I.rc[j], d1[j], d2[j],
                                                  K.l_t, K.theta, K.g0f);
             R.n1[j] = n.x;
             R.n2[j] = n.y;
@@ -209,7 +209,7 @@ RVDD_HD void eval_primal(const RowIn<V> &I, const IterConsts &K, const float (&d
 #else
 #pragma unroll
     for (int j = 0; j <= V; j++)
-        rvdd_primal_px(I.u1[j], I.u2[j], I.gx[j], I.gy[j], I.g2[j], I.rc[j], d1[j], d2[j], K.l_t, K.theta, K.g0f,
+        rvdd_primal_px(I.u1[j], I.u2[j], I.gx[j], I.gy[j], rvdd_grad2(I.gx[j], I.gy[j]), I.rc[j], d1[j], d2[j], K.l_t, K.theta, K.g0f,
                        &R.n1[j], &R.n2[j]);
 #endif
 #pragma unroll
@@ -347,38 +347,89 @@ RVDD_HD void cgrad_px(const float *I1, int x, int y, int nx, int ny, float *dx, 
     *dy = rvdd_half_diff(yd, yu);
 }
 
-// per-warp constants at pixel (x, y) (tvl1flow_lib.c:143-159): bicubic samples of I1, I1x, I1y at (x+u1, y+u2)
-// with border_out = true, then |grad|^2 and the constant part of rho.
-RVDD_HD void warp_consts_px(const float *I0, const float *I1, const float *I1x, const float *I1y, float a, float b,
-                            int x, int y, int nx, int ny, float *gx, float *gy, float *g2, float *rc)
+// per-warp constants (tvl1flow_lib.c:143-159) for U pixels at once: bicubic samples of I1, I1x, I1y at (x+u1, y+u2) with
+// border_out = true, then the constant part of rho (|grad|^2, :155, is recomputed by the iteration: rvdd_grad2).
+// The phase is a gather whose addresses depend on a load (the flow), so it is latency-bound unless many loads are in
+// flight: the routine is branch-free -- a sample that leaves the image (bicubic_interpolation.c:195-196 returns 0)
+// reads element 0 sixteen times through zero strides and is zeroed by a select -- so that the compiler can issue the
+// flow loads of all U pixels, then the 16 * U taps of each image, before the double-precision arithmetic starts.
+// idx[k] < 0 marks an unused slot.
+template <int U>
+RVDD_HD void warp_consts_eval(const float *I1, const float *I1x, const float *I1y, const float (&a)[U], const float (&b)[U],
+                              const float (&i0)[U], const int (&px)[U], const int (&py)[U], const bool (&act)[U], int nx,
+                              int ny, float *gx, float *gy, float *rc)
 {
-    const float uu = FADD((float)x, a), vv = FADD((float)y, b);
-    float w0 = 0.f, wx = 0.f, wy = 0.f;
-    if (rvdd_inside_strict(uu, vv, nx, ny)) {
-        const int bx = (int)uu, by = (int)vv;
-        const float tx = FSUB(uu, (float)bx), ty = FSUB(vv, (float)by);
-        const long long o = (long long)(by - 1) * nx + (bx - 1);
-        float v[4][4];
+    float tx[U], ty[U];
+    long long o[U];
+    int rs[U], cs[U];
+    bool in[U];
 #pragma unroll
-        for (int c = 0; c < 4; c++)
-#pragma unroll
-            for (int r = 0; r < 4; r++) v[c][r] = I1[o + r * nx + c];
-        w0 = rvdd_bicubic_cell(v, tx, ty);
-#pragma unroll
-        for (int c = 0; c < 4; c++)
-#pragma unroll
-            for (int r = 0; r < 4; r++) v[c][r] = I1x[o + r * nx + c];
-        wx = rvdd_bicubic_cell(v, tx, ty);
-#pragma unroll
-        for (int c = 0; c < 4; c++)
-#pragma unroll
-            for (int r = 0; r < 4; r++) v[c][r] = I1y[o + r * nx + c];
-        wy = rvdd_bicubic_cell(v, tx, ty);
+    for (int k = 0; k < U; k++) {
+        const float uu = FADD((float)px[k], a[k]), vv = FADD((float)py[k], b[k]);
+        in[k] = act[k] && rvdd_inside_strict(uu, vv, nx, ny);
+        const int bx = in[k] ? (int)uu : 1, by = in[k] ? (int)vv : 1;
+        tx[k] = FSUB(uu, (float)bx);
+        ty[k] = FSUB(vv, (float)by);
+        rs[k] = in[k] ? nx : 0;
+        cs[k] = in[k] ? 1 : 0;
+        o[k] = in[k] ? (long long)(by - 1) * nx + (bx - 1) : 0;
     }
-    *gx = wx;
-    *gy = wy;
-    *g2 = FADD(FMUL(wx, wx), FMUL(wy, wy));
-    *rc = FSUB(FSUB(FSUB(w0, FMUL(wx, a)), FMUL(wy, b)), I0[(long long)y * nx + x]);
+    float w0[U], wx[U], wy[U];
+#pragma unroll
+    for (int img = 0; img < 3; img++) {
+        const float *src = img == 0 ? I1 : (img == 1 ? I1x : I1y);
+        float v[U][4][4];
+#pragma unroll
+        for (int k = 0; k < U; k++)
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) v[k][c][r] = src[o[k] + r * rs[k] + c * cs[k]];
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            const float w = in[k] ? rvdd_bicubic_cell(v[k], tx[k], ty[k]) : 0.f;
+            if (img == 0) w0[k] = w;
+            else if (img == 1) wx[k] = w;
+            else wy[k] = w;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+        if (!act[k]) continue;
+        const long long i = (long long)py[k] * nx + px[k];
+        gx[i] = wx[k];
+        gy[i] = wy[k];
+        rc[i] = FSUB(FSUB(FSUB(w0[k], FMUL(wx[k], a[k])), FMUL(wy[k], b[k])), i0[k]);
+    }
+}
+
+// The same for U linear pixel indices (idx[k] < 0 marks an unused slot), loads included.
+template <int U>
+RVDD_HD void warp_consts_batch(const float *I0, const float *I1, const float *I1x, const float *I1y, const float *u1,
+                               const float *u2, const int (&idx)[U], int nx, int ny, float *gx, float *gy, float *rc)
+{
+    float a[U], b[U], i0[U];
+    int px[U], py[U];
+    bool act[U];
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+        act[k] = idx[k] >= 0;
+        const int i = act[k] ? idx[k] : 0;
+        a[k] = u1[i];
+        b[k] = u2[i];
+        i0[k] = I0[i];
+        py[k] = i / nx;
+        px[k] = i - py[k] * nx;
+    }
+    warp_consts_eval<U>(I1, I1x, I1y, a, b, i0, px, py, act, nx, ny, gx, gy, rc);
+}
+
+// single-pixel form (host-side tests)
+RVDD_HD void warp_consts_px(const float *I0, const float *I1, const float *I1x, const float *I1y, const float *u1,
+                            const float *u2, int i, int nx, int ny, float *gx, float *gy, float *rc)
+{
+    const int idx[1] = {i};
+    warp_consts_batch<1>(I0, I1, I1x, I1y, u1, u2, idx, nx, ny, gx, gy, rc);
 }
 
 // flow upsampling to the next finer level at fine pixel (x, y) (zoom.c:85-109 + tvl1flow_lib.c:431-432)

@@ -119,11 +119,12 @@ extern "C" int hs_tvl1flow(const float *I0, const float *I1, float *u, int nx0, 
 
     // solver
     const size_t PL = (n0 + 3) & ~(size_t)3;
-    std::vector<float> Sbuf(18 * PL, 0.f);
+    std::vector<float> Sbuf(RVDD_NPLANES * PL, 0.f);
     float *Sp = Sbuf.data();
-    float *I1x = Sp, *I1y = Sp + PL, *gx = Sp + 2 * PL, *gy = Sp + 3 * PL, *g2 = Sp + 4 * PL, *rc = Sp + 5 * PL;
-    float *ub[2][2] = {{Sp + 6 * PL, Sp + 7 * PL}, {Sp + 8 * PL, Sp + 9 * PL}};
-    float *pb[2][4] = {{Sp + 10 * PL, Sp + 11 * PL, Sp + 12 * PL, Sp + 13 * PL}, {Sp + 14 * PL, Sp + 15 * PL, Sp + 16 * PL, Sp + 17 * PL}};
+    float *I1x = Sp, *I1y = Sp + PL, *gx = Sp + RVDD_PL_C * PL, *gy = Sp + (RVDD_PL_C + 1) * PL, *rc = Sp + (RVDD_PL_C + 2) * PL;
+    float *ub[2][2] = {{Sp + RVDD_PL_U * PL, Sp + (RVDD_PL_U + 1) * PL}, {Sp + (RVDD_PL_U + 2) * PL, Sp + (RVDD_PL_U + 3) * PL}};
+    float *pb[2][4] = {{Sp + RVDD_PL_P * PL, Sp + (RVDD_PL_P + 1) * PL, Sp + (RVDD_PL_P + 2) * PL, Sp + (RVDD_PL_P + 3) * PL},
+                       {Sp + (RVDD_PL_P + 4) * PL, Sp + (RVDD_PL_P + 5) * PL, Sp + (RVDD_PL_P + 6) * PL, Sp + (RVDD_PL_P + 7) * PL}};
     int uc = 0, pc = 0;
     for (int s = S - 1; s >= 0; s--) {
         const int w_ = nx[s], h_ = ny[s], n = w_ * h_;
@@ -134,8 +135,15 @@ extern "C" int hs_tvl1flow(const float *I0, const float *I1, float *u, int nx0, 
             cgrad_px(J1, i % w_, i / w_, w_, h_, &I1x[i], &I1y[i]);
         }
         for (int w = 0; w < nwarps; w++) {
-            for (int i = 0; i < n; i++)
-                warp_consts_px(J0, J1, I1x, I1y, ub[uc][0][i], ub[uc][1][i], i % w_, i / w_, w_, h_, &gx[i], &gy[i], &g2[i], &rc[i]);
+            // the device walks the image with a stride (several pixels per thread); mimic that with a stride of 7
+            for (int i = 0; i < n; i += 14) {
+                int idx[2] = {i, i + 7 < n ? i + 7 : -1};
+                for (int k = 0; k < 7 && idx[0] < n && idx[0] < i + 7; k++) {
+                    warp_consts_batch<2>(J0, J1, I1x, I1y, ub[uc][0], ub[uc][1], idx, w_, h_, gx, gy, rc);
+                    idx[0]++;
+                    idx[1] = (idx[1] >= 0 && idx[1] + 1 < n && idx[1] + 1 < i + 14) ? idx[1] + 1 : -1;
+                }
+            }
             int it = 0;
             float err = INFINITY;
             while (err > eps2 && it < RVDD_MAX_ITERATIONS) {

@@ -133,6 +133,21 @@ RVDD_API int rvdd_warp_dev(const float *x_dev, const float *flow_dev, float *out
  * times `mul`. */
 RVDD_API int rvdd_upsample2_dev(const float *in_dev, float *out_dev, long long planes, int h, int w, float mul, void *stream);
 
+/* Hamilton-Adams demosaicking of packed Bayer raw, the step right before the warp in the inference loop
+ * (models/recurrent_model.py:126 -> util/Hamilton_Adam_demo.py:249-289, `HamiltonAdam(pattern).forward`), one kernel:
+ *   x_dev : [B][4][H][W] packed raw, plane k = CFA sample at cell position (k / 2, k % 2) (pack_in_one, :226-234);
+ *   y_dev : [B][3][2H][2W] RGB;
+ *   pattern: "grbg", "rggb", "gbrg" or "bggr" (colour of cell positions (0,0), (0,1), (1,0), (1,1); the model uses
+ *            "gbrg", recurrent_model.py:98).  A tensor [B, 4k, H, W] of k stacked frames is B*k images here. */
+RVDD_API int rvdd_demosaic_ha_dev(const float *x_dev, float *y_dev, int B, int H, int W, const char *pattern, void *stream);
+
+/* remosaick (Hamilton_Adam_demo.py:237-246) fused with the value mapping (v + add) * mul (singleiT, library.py:67:
+ * add = 1, mul = 0.5) and the mean over the 4 packed channels (library.py:165-167): the gray image the online-flow
+ * path (validate.py:29-33, --val_flow_from_denoised) hands to TV-L1, without leaving the GPU.
+ *   rgb_dev : [B][3][2H][2W];  gray_dev : [B][H][W]. */
+RVDD_API int rvdd_remosaick_gray_dev(const float *rgb_dev, float *gray_dev, int B, int H, int W, const char *pattern,
+                                     float add, float mul, void *stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * End-to-end with HOST buffers: exactly what data/base_dataset.py:159-180 does per (source, target) pair
  * (compute_flow_and_warp + the (h, w, 2) flow the .tif files hold), for a whole batch:

@@ -56,3 +56,14 @@ for (B, C, H, W) in [(1, 3, 1440, 2560), (1, 48, 1440, 2560), (4, 48, 720, 1280)
     rows.append(dict(shape=[B, C, H, W], ms=t_full, gbs=by / t_full / 1e6, frac=by / t_full / 1e6 / peak,
                      ms_fused_up2=t_half, ms_white_noise_flow=t_rough, ms_torch_grid_sample=t_ref))
     print(json.dumps(rows[-1]))
+
+# Hamilton-Adams demosaic (csrc/demosaic.cu): 4 B read + 12 B written per full-resolution pixel
+for (B, H, W) in [(1, 720, 1280), (8, 720, 1280), (1, 1080, 1920)]:
+    x = torch.rand(B, 4, H, W, device="cuda") * 2 - 1
+    by = 16.0 * B * 4 * H * W
+    t = timeit(lambda: br.demosaic(x, "gbrg"))
+    rgb = br.demosaic(x, "gbrg")
+    t2 = timeit(lambda: br.remosaick_gray(rgb, "gbrg"))
+    rows.append(dict(kernel="demosaic_ha", packed_shape=[B, 4, H, W], ms=t, gbs=by / t / 1e6, frac=by / t / 1e6 / peak,
+                     remosaick_gray_ms=t2, remosaick_gray_gbs=(4.0 * B * H * W * 5) / t2 / 1e6))
+    print(json.dumps(rows[-1]))

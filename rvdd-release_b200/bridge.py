@@ -44,6 +44,9 @@ _SIGNATURES = {
     "rvdd_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
     "rvdd_profile_scales": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
     "rvdd_profile_phases": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
+    "rvdd_demosaic_ha_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_void_p]),
+    "rvdd_remosaick_gray_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_float,
+                                          C.c_float, C.c_void_p]),
     "rvdd_selftest_fastmath": (C.c_int, [C.c_ulonglong, C.c_int, C.c_int, C.POINTER(C.c_ulonglong)]),
     "rvdd_debug_level_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "rvdd_warp_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -225,6 +228,30 @@ class Bridge:
         out = torch.empty((*rem, c, 2 * h, 2 * w), dtype=torch.float32, device=t.device)
         self._ck(self.lib.rvdd_upsample2_dev(t.data_ptr(), out.data_ptr(), planes, h, w, float(mul),
                                              _stream_ptr(t.device)))
+        return out
+
+    def demosaic(self, x, pattern="gbrg"):
+        """HamiltonAdam(pattern).forward (util/Hamilton_Adam_demo.py:249-289): [B, 4k, H, W] packed raw -> [B, 3k, 2H, 2W]."""
+        _check_cuda_f32(x, "x")
+        x = x.contiguous()
+        B, c4, H, W = x.shape
+        if c4 % 4:
+            raise BridgeError("demosaic: the channel count must be a multiple of 4 (packed Bayer frames)")
+        out = torch.empty((B, 3 * (c4 // 4), 2 * H, 2 * W), dtype=torch.float32, device=x.device)
+        self._ck(self.lib.rvdd_demosaic_ha_dev(x.data_ptr(), out.data_ptr(), B * (c4 // 4), H, W, pattern.encode(),
+                                               _stream_ptr(x.device)))
+        return out
+
+    def remosaick_gray(self, rgb, pattern="gbrg", add=1.0, mul=0.5):
+        """mean over the 4 packed channels of (remosaick(rgb) + add) * mul: [B, 3, 2H, 2W] -> [B, H, W]."""
+        _check_cuda_f32(rgb, "rgb")
+        rgb = rgb.contiguous()
+        B, c, H2, W2 = rgb.shape
+        if c != 3 or H2 % 2 or W2 % 2:
+            raise BridgeError("remosaick_gray: expected [B, 3, 2H, 2W]")
+        out = torch.empty((B, H2 // 2, W2 // 2), dtype=torch.float32, device=rgb.device)
+        self._ck(self.lib.rvdd_remosaick_gray_dev(rgb.data_ptr(), out.data_ptr(), B, H2 // 2, W2 // 2, pattern.encode(),
+                                                  float(add), float(mul), _stream_ptr(rgb.device)))
         return out
 
     # ------------------------------------------------------------------ host entry point (end to end)

@@ -14,7 +14,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-SOURCES = ["bridge.cu", "prep.cu", "solver.cu", "warp.cu", "selftest.cu"]
+SOURCES = ["bridge.cu", "prep.cu", "solver.cu", "warp.cu", "demosaic.cu", "selftest.cu"]
 LIB = os.path.join(PKG, "lib", "libBridge.so")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

@@ -527,6 +527,43 @@ extern "C" int rvdd_upsample2_dev(const float *in, float *out, long long planes,
     return 0;
 }
 
+// Bayer pattern string ('grbg', 'rggb', 'gbrg', 'bggr': colour of cell positions (0,0), (0,1), (1,0), (1,1), as in
+// Hamilton_Adam_demo.py:201-224) -> positions of the red and blue samples
+static int parse_pattern(const char *pattern, int *ry, int *rx, int *by, int *bx)
+{
+    if (!pattern || strlen(pattern) != 4) return -1;
+    int nr = 0, nb = 0, ng = 0;
+    for (int k = 0; k < 4; k++) {
+        if (pattern[k] == 'r') { *ry = k >> 1; *rx = k & 1; nr++; }
+        else if (pattern[k] == 'b') { *by = k >> 1; *bx = k & 1; nb++; }
+        else if (pattern[k] == 'g') ng++;
+    }
+    return (nr == 1 && nb == 1 && ng == 2 && *ry != *by && *rx != *bx) ? 0 : -1;
+}
+
+extern "C" int rvdd_demosaic_ha_dev(const float *x, float *y, int B, int H, int W, const char *pattern, void *stream)
+{
+    if (!x || !y) return fail("rvdd_demosaic_ha_dev: null argument");
+    if (B < 0 || H < 1 || W < 1 || B > 65535) return fail("rvdd_demosaic_ha_dev: bad geometry");
+    int ry = 0, rx = 0, by = 0, bx = 0;
+    if (parse_pattern(pattern, &ry, &rx, &by, &bx)) return fail("rvdd_demosaic_ha_dev: pattern must be grbg, rggb, gbrg or bggr");
+    if (B == 0) return 0;
+    CK(launch_demosaic_ha(x, y, B, H, W, ry, rx, by, bx, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int rvdd_remosaick_gray_dev(const float *rgb, float *gray, int B, int H, int W, const char *pattern, float add,
+                                       float mul, void *stream)
+{
+    if (!rgb || !gray) return fail("rvdd_remosaick_gray_dev: null argument");
+    if (B < 0 || H < 1 || W < 1 || B > 65535 || H > 65535) return fail("rvdd_remosaick_gray_dev: bad geometry");
+    int ry = 0, rx = 0, by = 0, bx = 0;
+    if (parse_pattern(pattern, &ry, &rx, &by, &bx)) return fail("rvdd_remosaick_gray_dev: pattern must be grbg, rggb, gbrg or bggr");
+    if (B == 0) return 0;
+    CK(launch_remosaick_gray(rgb, gray, B, H, W, ry, rx, by, bx, add, mul, (cudaStream_t)stream));
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ host entry points
 
 // planar [2][n] -> chunky [n][2] (library.py:175 returns the (h, w, 2) view; base_dataset.py:180 writes it)

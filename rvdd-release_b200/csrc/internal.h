@@ -82,4 +82,9 @@ struct WarpArgs {
 cudaError_t launch_warp(const WarpArgs &a, cudaStream_t st);
 cudaError_t launch_upsample2(const float *in, float *out, long long planes, int h, int w, float mul, cudaStream_t st);
 
+// demosaic.cu: (ry, rx) / (by, bx) = position of the red / blue sample inside the 2x2 Bayer cell
+cudaError_t launch_demosaic_ha(const float *x, float *y, int B, int H, int W, int ry, int rx, int by, int bx, cudaStream_t st);
+cudaError_t launch_remosaick_gray(const float *rgb, float *gray, int B, int H, int W, int ry, int rx, int by, int bx,
+                                  float add, float mul, cudaStream_t st);
+
 }  // namespace rvdd

@@ -122,18 +122,21 @@ __global__ void __launch_bounds__(256) warp_kernel(const WarpArgs a)
 //
 // warp_kernel issues 16 scattered global loads per pixel and channel; a warp's 32 pixels touch the same ~5 cache lines
 // 16 times over, and the kernel ends up bound by L1 wavefronts at ~0.8 TB/s of useful traffic.  For plane-contiguous
-// inputs (NCHW, xs_w == 1) the tiled kernel below stages, per 32x8 output tile and per group of 8 channels, the
-// bounding box of all taps of the tile in shared memory with coalesced row loads and gathers from there (conflict-free:
-// a warp's lanes read consecutive words).  The sampling position, the 16 clamped tap offsets and the 8 cubic weights
-// are computed once per pixel and reused for every channel.  If the flow varies so much inside a tile that the box
-// does not fit (more than 13 px horizontally / 13 px vertically), the tile falls back to direct global gathers.
-// Same arithmetic as warp_kernel, hence bit-identical results.
+// inputs (NCHW, xs_w == 1) the tiled kernel below stages, per 32x8 output tile and per group of 4 channels, the
+// bounding box of all taps of the tile in shared memory and gathers from there.  The staged box is CHANNEL-INTERLEAVED
+// (one float4 = the 4 channels of a pixel): a tap is ONE 128-bit shared-memory load for 4 channels instead of four
+// 32-bit ones, always 16-byte aligned whatever the flow, and conflict-free (the lanes of a quarter-warp read
+// consecutive 16-byte words; the row pitch is a multiple of 128 B, so lanes whose taps fall on different rows still
+// hit different banks).  The sampling position, the clamped tap offsets and the cubic weights are computed once per
+// pixel and reused for every channel; the next channel group streams in with cp.async while the current one is
+// consumed.  If the flow varies so much inside a tile that the box does not fit (more than 13 px horizontally or
+// vertically), the tile falls back to direct global gathers.  Same arithmetic as warp_kernel.
 
 #define WT_X 32
 #define WT_Y 8
 #define WT_BW 48            // staged box: at most 48 x 24 pixels
 #define WT_BH 24
-#define WT_CC 4             // channels staged per pass (two passes in flight: cp.async double buffering)
+#define WT_CC 4             // channels staged per pass = one float4 (two passes in flight: cp.async double buffering)
 
 __device__ __forceinline__ void cp_async4(float *dst_smem, const float *src)
 {
@@ -145,7 +148,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 template <int INTERP>
 __global__ void __launch_bounds__(256) warp_tile_kernel(const WarpArgs a)
 {
-    __shared__ float s_box[2][WT_CC][WT_BH * WT_BW];
+    __shared__ float4 s_box[2][WT_BH * WT_BW];
     __shared__ int s_lim[4];
     const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
     const int x = blockIdx.x * WT_X + lane, y = blockIdx.y * WT_Y + wy, b = blockIdx.z;
@@ -224,7 +227,7 @@ __global__ void __launch_bounds__(256) warp_tile_kernel(const WarpArgs a)
                 const float *q = p + (long long)ty[r] * a.xs_h;
                 float row = 0.f;
 #pragma unroll
-                for (int k = 0; k < NT; k++) row = (INTERP == 1) ? row + __ldg(q + tx[k]) * cx[k] : row + __ldg(q + tx[k]) * cx[k];
+                for (int k = 0; k < NT; k++) row = row + __ldg(q + tx[k]) * cx[k];
                 acc += row * cy[r];
             }
             ob[(long long)c * a.os_c] = acc;
@@ -237,15 +240,21 @@ __global__ void __launch_bounds__(256) warp_tile_kernel(const WarpArgs a)
 #pragma unroll
         for (int k = 0; k < NT; k++) off[r][k] = (ty[r] - by0) * WT_BW + (tx[k] - bx0);
 
-    // stage the box of WT_CC channels starting at c0 into buffer `buf` (asynchronous global -> shared copies)
+    // stage the box of the 4 channels starting at c0 into buffer `buf`.  A lane owns (column lane / 4, channel lane % 4):
+    // a warp reads 8 consecutive pixels (one full 32-byte sector) of each of the 4 channel planes and writes 32
+    // consecutive floats of the interleaved box -- conflict-free stores, fully used sectors.
+    const int s_cc = lane & 3, s_col = lane >> 2;
     auto stage = [&](int c0, int buf) {
-        const int nc = min(WT_CC, a.C - c0);
-        for (int cc = 0; cc < nc; cc++) {
-            const float *p = xb + (long long)(c0 + cc) * a.xs_c + (long long)by0 * a.xs_h + bx0;
+        float *dst = reinterpret_cast<float *>(s_box[buf]);
+        if (c0 + s_cc < a.C) {
+            const float *p = xb + (long long)(c0 + s_cc) * a.xs_c + (long long)by0 * a.xs_h + bx0;
             for (int r = wy; r < bh; r += WT_Y) {
                 const float *q = p + (long long)r * a.xs_h;
-                if (lane < bw) cp_async4(&s_box[buf][cc][r * WT_BW + lane], q + lane);
-                if (lane + 32 < bw) cp_async4(&s_box[buf][cc][r * WT_BW + lane + 32], q + lane + 32);
+#pragma unroll
+                for (int col0 = 0; col0 < WT_BW; col0 += 8) {
+                    const int col = col0 + s_col;
+                    if (col < bw) cp_async4(dst + (r * WT_BW + col) * 4 + s_cc, q + col);
+                }
             }
         }
         cp_async_commit();
@@ -259,22 +268,31 @@ __global__ void __launch_bounds__(256) warp_tile_kernel(const WarpArgs a)
         if (more) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncthreads();
         if (inside) {
-            for (int cc = 0; cc < nc; cc++) {
-                const float *sb = s_box[buf][cc];
-                float acc = 0.f;
-                if (INTERP == 1) {
+            const float4 *sb = s_box[buf];
+            float4 acc;
+            if (INTERP == 1) {
+                acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int r = 0; r < NT; r++) {
-                        const float row = sb[off[r][0]] * cx[0] + sb[off[r][1]] * cx[1] + sb[off[r][NT - 2]] * cx[NT - 2] +
-                                          sb[off[r][NT - 1]] * cx[NT - 1];
-                        acc += row * cy[r];
-                    }
-                } else {
-                    acc = sb[off[0][0]] * (cx[0] * cy[0]) + sb[off[0][NT - 1]] * (cx[NT - 1] * cy[0]) +
-                          sb[off[NT - 1][0]] * (cx[0] * cy[NT - 1]) + sb[off[NT - 1][NT - 1]] * (cx[NT - 1] * cy[NT - 1]);
+                for (int r = 0; r < NT; r++) {
+                    const float4 v0 = sb[off[r][0]], v1 = sb[off[r][1]], v2 = sb[off[r][NT - 2]], v3 = sb[off[r][NT - 1]];
+                    acc.x += (v0.x * cx[0] + v1.x * cx[1] + v2.x * cx[NT - 2] + v3.x * cx[NT - 1]) * cy[r];
+                    acc.y += (v0.y * cx[0] + v1.y * cx[1] + v2.y * cx[NT - 2] + v3.y * cx[NT - 1]) * cy[r];
+                    acc.z += (v0.z * cx[0] + v1.z * cx[1] + v2.z * cx[NT - 2] + v3.z * cx[NT - 1]) * cy[r];
+                    acc.w += (v0.w * cx[0] + v1.w * cx[1] + v2.w * cx[NT - 2] + v3.w * cx[NT - 1]) * cy[r];
                 }
-                ob[(long long)(c0 + cc) * a.os_c] = acc;
+            } else {
+                const float4 v00 = sb[off[0][0]], v01 = sb[off[0][NT - 1]], v10 = sb[off[NT - 1][0]], v11 = sb[off[NT - 1][NT - 1]];
+                const float w00 = cx[0] * cy[0], w01 = cx[NT - 1] * cy[0], w10 = cx[0] * cy[NT - 1], w11 = cx[NT - 1] * cy[NT - 1];
+                acc.x = v00.x * w00 + v01.x * w01 + v10.x * w10 + v11.x * w11;
+                acc.y = v00.y * w00 + v01.y * w01 + v10.y * w10 + v11.y * w11;
+                acc.z = v00.z * w00 + v01.z * w01 + v10.z * w10 + v11.z * w11;
+                acc.w = v00.w * w00 + v01.w * w01 + v10.w * w10 + v11.w * w11;
             }
+            float *o = ob + (long long)c0 * a.os_c;
+            o[0] = acc.x;
+            if (nc > 1) o[a.os_c] = acc.y;
+            if (nc > 2) o[2 * a.os_c] = acc.z;
+            if (nc > 3) o[3 * a.os_c] = acc.w;
         }
         __syncthreads();                                   // this buffer is refilled two passes from now
     }

@@ -98,10 +98,13 @@ def compute_flows_from_denoised(denoised, noisy_packed, predemosaic=True):
     returns      : [1, 1, 2, H, W] flow (source = denoised frame, target = noisy frame), the layout of data['flow']
     """
     b = _bridge.default_bridge()
-    src = remosaick(denoised) if predemosaic else denoised
-    # singleiT of library.py:67: (x + 1) / 2, CHW -> HWC
-    pair = torch.cat((noisy_packed[:1], src[:1]), 0)
-    pair = ((pair + 1.) / 2.).permute(0, 2, 3, 1).contiguous()
-    gray = b.gray(pair)                                          # mean of the 4 channels (library.py:165-167)
+    if predemosaic:
+        # remosaick + singleiT of library.py:67 ((x + 1) / 2) + mean of the 4 packed channels (library.py:165-167), fused
+        g_src = b.remosaick_gray(denoised[:1], "gbrg", add=1.0, mul=0.5)
+        g_tgt = b.gray(((noisy_packed[:1] + 1.) / 2.).permute(0, 2, 3, 1).contiguous())
+        gray = torch.cat((g_tgt, g_src), 0)
+    else:
+        pair = torch.cat((noisy_packed[:1], denoised[:1]), 0)
+        gray = b.gray(((pair + 1.) / 2.).permute(0, 2, 3, 1).contiguous())
     flow = b.tvl1_flow(gray, src=[1], tgt=[0])                   # target = noisy frame, source = denoised frame
     return flow.unsqueeze(0)

@@ -3,6 +3,7 @@ container, where /root/reference exists; the committed .npz files are what trave
 
 * tvl1_*.npz   : inputs + flow of the unmodified reference C (oracle/_ref/libref_serial.so, symbol tvl1flow of
                  libBridge.cpp:44) and the per-stage outputs of its exported functions, on small seeded inputs.
+* demosaic_*.npz: inputs + outputs of the reference's util/Hamilton_Adam_demo.py (HamiltonAdam.forward / remosaick).
 * warp_*.npz   : inputs + outputs of the reference's own util/flow_utils.py (warp, upsample_factor_2) imported from
                  /root/reference and run on the CPU with this image's torch.
 
@@ -57,6 +58,31 @@ def warp_golden():
         print(name, float(yb.abs().mean()))
 
 
+def demosaic_golden():
+    """util/Hamilton_Adam_demo.py of the reference, imported and run on the CPU."""
+    sys.path.insert(0, "/root/reference")
+    from util.Hamilton_Adam_demo import HamiltonAdam
+    g = torch.Generator().manual_seed(3)
+    for name, (B, k, H, W, pattern) in {"demosaic_gbrg": (2, 1, 18, 26, "gbrg"), "demosaic_gbrg_2frames": (1, 2, 9, 35, "gbrg"),
+                                        "demosaic_rggb": (1, 1, 11, 8, "rggb"), "demosaic_grbg": (1, 1, 6, 7, "grbg"),
+                                        "demosaic_bggr": (1, 1, 5, 16, "bggr")}.items():
+        # smooth image + noise in the network's [-1, 1] range, sampled through the CFA
+        yy, xx = torch.meshgrid(torch.arange(2 * H, dtype=torch.float32), torch.arange(2 * W, dtype=torch.float32), indexing="ij")
+        base = 0.6 * torch.sin(0.21 * xx + 0.13 * yy) * torch.cos(0.17 * yy - 0.05 * xx)
+        x = torch.empty(B, 4 * k, H, W)
+        for b in range(B):
+            for j in range(4 * k):
+                x[b, j] = base[(j % 4) // 2::2, (j % 4) % 2::2] + 0.1 * torch.randn(H, W, generator=g) + 0.05 * (j // 4)
+        ha = HamiltonAdam(pattern)
+        with torch.no_grad():
+            y = ha(x)
+            r = ha.remosaick(y[:, :3])
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), x=x.numpy(), y=y.numpy(), remosaick=r.numpy(),
+                            pattern=np.array(pattern))
+        print(name, float(y.abs().mean()))
+
+
 if __name__ == "__main__":
     tvl1_golden()
     warp_golden()
+    demosaic_golden()

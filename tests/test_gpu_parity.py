@@ -320,3 +320,39 @@ def test_precompute_driver_on_gpu(tmp_path, bridge, port):
         fut = flowio.read_tif(str(tmp_path / "flow" / ("seq%d" % v) / "003_002.tif"))         # future source 003 -> target 002
         assert np.array_equal(fut.transpose(2, 0, 1), port.tvl1flow(g[2], g[3]))
     assert precompute.precompute_dataset(listed, str(tmp_path / "flow"), None, 2, 1) == []    # resume: nothing to do
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "demosaic_*.npz"))))
+def test_demosaic_matches_reference_golden(bridge, path):
+    """Hamilton-Adams kernel against the reference's own module output (util/Hamilton_Adam_demo.py:249-289)."""
+    from rvdd_release_b200.hamilton_adam import HamiltonAdam
+    g = np.load(path)
+    ha = HamiltonAdam(str(g["pattern"]))
+    y = ha(torch.from_numpy(g["x"]).cuda())
+    assert tuple(y.shape) == g["y"].shape
+    assert float((y.cpu() - torch.from_numpy(g["y"])).abs().max()) <= 1e-6
+    r = ha.remosaick(torch.from_numpy(g["y"][:, :3]).cuda())
+    assert torch.equal(r.cpu(), torch.from_numpy(g["remosaick"]))
+
+
+@pytest.mark.parametrize("H,W,pattern", [(720, 1280, "gbrg"), (33, 47, "gbrg"), (1, 1, "gbrg"), (2, 70, "rggb"), (45, 3, "bggr"),
+                                         (16, 32, "grbg")])
+def test_demosaic_against_oracle_sizes(bridge, H, W, pattern):
+    """Full pipeline size (1440 x 2560 output), ragged tiles, a single Bayer cell: bit-level agreement with the oracle."""
+    from oracle import demosaic_ref
+    seq = synth.sequence(2, H, W, "iso3200", noise_seed=5)
+    x = (2.0 * (seq / 4095.0) - 1.0).permute(0, 3, 1, 2).contiguous()                  # [2, 4, H, W] in [-1, 1]
+    y = bridge.demosaic(x.cuda(), pattern).cpu().numpy()
+    ref = demosaic_ref.hamilton_adam(x.numpy(), pattern)
+    assert y.shape == ref.shape == (2, 3, 2 * H, 2 * W)
+    assert np.abs(y - ref).max() <= 1e-6
+    # stacked frames [1, 8, H, W] are demosaicked frame by frame (recurrent_model.py:126 passes 4k channels)
+    y2 = bridge.demosaic(x.reshape(1, 8, H, W).cuda(), pattern).cpu().numpy()
+    assert np.array_equal(y2.reshape(2, 3, 2 * H, 2 * W), y)
+    # remosaick + (x + 1) / 2 + mean of 4, fused, against the oracle's remosaick and numpy
+    gray = bridge.remosaick_gray(torch.from_numpy(ref).cuda(), pattern, add=1.0, mul=0.5).cpu().numpy()
+    packed = (demosaic_ref.remosaick(ref, pattern) + np.float32(1)) / np.float32(2)
+    want = (((packed[:, 0] + packed[:, 1]) + packed[:, 2]) + packed[:, 3]) * np.float32(0.25)
+    assert np.array_equal(gray, want)
+    if pattern == "gbrg":     # the CFA samples survive demosaic -> remosaick untouched
+        assert np.array_equal(demosaic_ref.remosaick(y, pattern), x.numpy())

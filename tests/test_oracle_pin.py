@@ -80,3 +80,40 @@ def test_warp_ref_matches_reference_golden(path):
     # independent numpy restatement of the ATen semantics (A = -0.75, centre unclipped, taps clamped)
     man = warp_ref.grid_sample_manual(g["x"][0].astype(np.float64), g["flow"][0])
     assert np.abs(man - g["bicubic"][0]).max() < 2e-4 * max(1.0, np.abs(g["bicubic"]).max())
+
+
+def test_oracle_reproduces_reference_pipeline_psnr(port):
+    """The end-to-end fixture (tests/golden/make_pipeline_golden.py: reference flows, reference warp, shipped
+    recurrent-convunet-iso3200 checkpoint) replayed on the CPU with the ORACLE's flow and warp in the loop: same flows
+    bit for bit, same PSNR per frame.  The GPU test (test_gpu_pipeline.py) runs the same loop with the CUDA path."""
+    d = np.load(os.path.join(GOLDEN, "pipeline_convunet_iso3200.npz"))
+    net = torch.jit.load(os.path.join(GOLDEN, "pipeline_convunet_iso3200_denoiser.pt"), map_location="cpu").eval()
+    ha = torch.jit.load(os.path.join(GOLDEN, "pipeline_hamilton_adams_gbrg_48x80.pt"), map_location="cpu").eval()
+    nfr, h, w = (int(v) for v in d["geometry"])
+    seq = synth.sequence(nfr, h, w, "iso3200")
+    assert float(seq.numpy().astype(np.float64).sum()) == float(d["frames_checksum"])
+    g = np.mean(seq.numpy(), axis=3)
+    gt = torch.from_numpy(d["gt"].astype(np.float32))[:, None].repeat(1, 3, 1, 1)
+    with torch.no_grad():
+        n = [ha((2.0 * (seq[t] / 4095.0) - 1.0).permute(2, 0, 1)[None].contiguous()) for t in range(nfr)]
+        lastden, psnrs = n[0], []
+        for t in range(1, nfr):
+            flow = port.tvl1flow(g[t], g[t - 1])
+            assert np.array_equal(flow.transpose(1, 2, 0), d["flows"][t - 1])
+            up = warp_ref.upsample_factor_2(torch.from_numpy(flow[None]), 2)
+            warped, _ = warp_ref.warp(lastden, up, "bicubic")
+            den = net(torch.cat((warped, n[t]), 1))
+            lastden = den.clone()
+            psnrs.append(float(10 * torch.log10(4.0 / torch.mean((den - gt[t:t + 1]) ** 2))))
+    assert np.max(np.abs(np.array(psnrs) - d["psnr"])) <= 1e-3
+    assert float((den[0] - torch.from_numpy(d["denoised_last"])).abs().max()) <= 1e-5
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "demosaic_*.npz"))))
+def test_demosaic_ref_matches_reference_golden(path):
+    """oracle/demosaic_ref.py against vectors produced by the reference's own HamiltonAdam module (all 4 patterns)."""
+    from oracle import demosaic_ref
+    g = np.load(path)
+    y = demosaic_ref.hamilton_adam(g["x"], str(g["pattern"]))
+    assert y.shape == g["y"].shape and np.abs(y - g["y"]).max() <= 1e-6
+    assert np.array_equal(demosaic_ref.remosaick(g["y"][:, :3], "gbrg"), g["remosaick"])

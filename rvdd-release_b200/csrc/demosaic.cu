@@ -15,8 +15,8 @@
 
 namespace rvdd {
 
-#define DM_TW 64                      // output tile width
-#define DM_TH 16                      // output tile height
+#define DM_TW 64                      // output tile: 64 x 16 pixels = 32 x 8 Bayer cells, one cell per thread
+#define DM_TH 16
 #define DM_PW (DM_TW + 6)             // CFA tile with a 3 pixel halo
 #define DM_PH (DM_TH + 6)
 #define DM_GW (DM_TW + 2)             // green tile with a 1 pixel halo
@@ -26,99 +26,129 @@ struct DemosaicArgs {
     const float *x;                   // [B][4][H][W] packed raw
     float *y;                         // [B][3][2H][2W]
     int B, H, W;
-    int ry, rx, by, bx;               // position of the red / blue sample inside the 2x2 cell
 };
 
 __device__ __forceinline__ float sgn(float v) { return (float)((v > 0.f) - (v < 0.f)); }     // torch.sign
 
+// green at a red / blue pixel (algorithm 1, Hamilton_Adam_demo.py:123-142).  p points at the pixel inside the staged
+// CFA tile, whose halo already holds the replicated border (ReplicationPad2d((2, 2, 2, 2))); PW = tile pitch.
+template <int PW> __device__ __forceinline__ float green_at(const float *p)
+{
+    const float c = p[0], l1 = p[-1], r1 = p[1], u1 = p[-PW], d1 = p[PW];
+    const float kh = 0.5f * l1 + 0.5f * r1, kv = 0.5f * u1 + 0.5f * d1;
+    const float dh = (p[-2] + -2.f * c) + p[2], dv = (p[-2 * PW] + -2.f * c) + p[2 * PW];
+    const float rawh = kh - dh / 4.f, rawv = kv - dv / 4.f;
+    const float clh = fabsf(l1 - r1) + fabsf(dh), clv = fabsf(u1 - d1) + fabsf(dv);
+    const float s = sgn(clh - clv);
+    return (1.f + s) * rawv / 2.f + (1.f - s) * rawh / 2.f;
+}
+
+// One CTA = one 64 x 16 output tile; one thread = one 2x2 Bayer cell.
+//   phase 1: CFA tile + 3 pixel halo into shared memory (pack_in_one, :226-234; clamped coordinates = replication)
+//   phase 2: green at every red / blue position of the tile + 1 pixel halo (positions outside the image take the green
+//            of the clamped position, which is what the replication padding in front of conv_algo2_green produces)
+//   phase 3: per cell, the missing colours from the colour differences (algorithm 2, :145-172) and the output.
+// In algorithm 2 the reference convolves the CFA MASKED to one colour, replication-padded: a neighbour contributes its
+// CFA value if it lies inside the image and zero if the padding replicated a pixel of another colour -- at a pixel
+// whose neighbours in that direction carry the colour, "outside the image" is exactly that case.
+// RY, RX: position of the red sample inside the 2x2 cell (blue sits on the opposite corner); compile-time so that the
+// per-cell colour arrays stay in registers.
+template <int RY, int RX>
 __global__ void __launch_bounds__(256) demosaic_ha_kernel(const DemosaicArgs a)
 {
-    __shared__ float P[DM_PH][DM_PW + 1];
-    __shared__ float G[DM_GH][DM_GW + 1];
+    constexpr int BY = 1 - RY, BX = 1 - RX;
+    __shared__ float P[DM_PH][DM_PW];
+    __shared__ float G[DM_GH][DM_GW];
     const int H2 = 2 * a.H, W2 = 2 * a.W;
     const int X0 = blockIdx.x * DM_TW, Y0 = blockIdx.y * DM_TH;
     const float *xb = a.x + (long long)blockIdx.z * 4 * a.H * a.W;
     const long long plane = (long long)a.H * a.W;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
 
-    // CFA tile: pack_in_one (Hamilton_Adam_demo.py:226-234), clamped coordinates = ReplicationPad2d
-    for (int i = threadIdx.x; i < DM_PH * DM_PW; i += 256) {
-        const int ty = i / DM_PW, tx = i - ty * DM_PW;
-        const int yy = min(max(Y0 + ty - 3, 0), H2 - 1), xx = min(max(X0 + tx - 3, 0), W2 - 1);
-        P[ty][tx] = xb[(long long)((yy & 1) * 2 + (xx & 1)) * plane + (long long)(yy >> 1) * a.W + (xx >> 1)];
-    }
-    __syncthreads();
-
-    // green on the tile + 1 pixel halo (algorithm 1, :123-142).  The halo positions are clamped to the image, which is
-    // what the replication padding in front of conv_algo2_green sees.
-    for (int i = threadIdx.x; i < DM_GH * DM_GW; i += 256) {
-        const int gy = i / DM_GW, gx = i - gy * DM_GW;
-        const int yy = min(max(Y0 + gy - 1, 0), H2 - 1), xx = min(max(X0 + gx - 1, 0), W2 - 1);
-        // neighbours of (yy, xx) in the CFA, clamped (ReplicationPad2d((2, 2, 2, 2)))
-        auto cfa = [&](int dy, int dx) {
-            const int y2 = min(max(yy + dy, 0), H2 - 1), x2 = min(max(xx + dx, 0), W2 - 1);
-            return P[y2 - Y0 + 3][x2 - X0 + 3];
-        };
-        const float c = cfa(0, 0);
-        const bool is_r = ((yy & 1) == a.ry) && ((xx & 1) == a.rx), is_b = ((yy & 1) == a.by) && ((xx & 1) == a.bx);
-        float g = c;
-        if (is_r || is_b) {
-            const float l1 = cfa(0, -1), r1 = cfa(0, 1), u1 = cfa(-1, 0), d1 = cfa(1, 0);
-            const float kh = 0.5f * l1 + 0.5f * r1, kv = 0.5f * u1 + 0.5f * d1;
-            const float dh = (cfa(0, -2) + -2.f * c) + cfa(0, 2), dv = (cfa(-2, 0) + -2.f * c) + cfa(2, 0);
-            const float rawh = kh - dh / 4.f, rawv = kv - dv / 4.f;
-            const float clh = fabsf(l1 - r1) + fabsf(dh), clv = fabsf(u1 - d1) + fabsf(dv);
-            const float s = sgn(clh - clv);
-            g = (1.f + s) * rawv / 2.f + (1.f - s) * rawh / 2.f;
-        }
-        G[gy][gx] = g;
-    }
-    __syncthreads();
-
-    // red and blue (algorithm 2, :145-172) and the three output planes
-    float *yb = a.y + (long long)blockIdx.z * 3 * H2 * W2;
-    for (int i = threadIdx.x; i < DM_TH * DM_TW; i += 256) {
-        const int ty = i / DM_TW, tx = i - ty * DM_TW;
-        const int yy = Y0 + ty, xx = X0 + tx;
-        if (yy >= H2 || xx >= W2) continue;
-        const float g = G[ty + 1][tx + 1];
-        // green second differences (conv_algo2_green): clamped neighbours are already in the halo
-        auto gr = [&](int dy, int dx) { return G[ty + 1 + dy][tx + 1 + dx]; };
-        const float gdh = (0.25f * gr(0, -1) + -0.5f * g) + 0.25f * gr(0, 1);
-        const float gdv = (0.25f * gr(-1, 0) + -0.5f * g) + 0.25f * gr(1, 0);
-        const float gdp = (gr(-1, -1) + -2.f * g) + gr(1, 1);
-        const float gdn = (gr(-1, 1) + -2.f * g) + gr(1, -1);
-        const int py = yy & 1, px = xx & 1;
-        float out[2];
+    // ---- phase 1
+    for (int ty = wrp; ty < DM_PH; ty += 8) {
+        const int yy = min(max(Y0 + ty - 3, 0), H2 - 1);
+        const float *row = xb + (long long)((yy & 1) * 2) * plane + (long long)(yy >> 1) * a.W;
 #pragma unroll
-        for (int ch = 0; ch < 2; ch++) {
-            // ch 0: red (mode 1), ch 1: blue (mode 2, Gr / Gb swapped, the "other" channel is red)
-            const int cy = ch ? a.by : a.ry, cx = ch ? a.bx : a.rx;      // where this colour is sampled
-            const int oy = ch ? a.ry : a.by, ox = ch ? a.rx : a.bx;      // where the other colour is sampled
-            // masked CFA of this colour with replication padding: value at the clamped position if that position
-            // carries this colour, else 0
-            auto m = [&](int dy, int dx) {
-                const int y2 = min(max(yy + dy, 0), H2 - 1), x2 = min(max(xx + dx, 0), W2 - 1);
-                return (((y2 & 1) == cy) && ((x2 & 1) == cx)) ? P[y2 - Y0 + 3][x2 - X0 + 3] : 0.f;
-            };
-            const bool on_row = (py == cy) && (px != cx);       // green pixel on this colour's row   (maskGr for red)
-            const bool on_col = (py != cy) && (px == cx);       // green pixel on this colour's column (maskGb for red)
-            const bool on_other = (py == oy) && (px == ox);     // pixel of the other colour          (mask_ochan)
-            float v = 0.f;
-            if (on_other) {
-                const float a00 = m(-1, -1), a22 = m(1, 1), a02 = m(-1, 1), a20 = m(1, -1);
-                const float cp = (0.5f * a00 + 0.5f * a22) - gdp / 4.f, cn = (0.5f * a02 + 0.5f * a20) - gdn / 4.f;
-                const float clp = fabsf(-a00 + a22) + fabsf(gdp), cln = fabsf(-a02 + a20) + fabsf(gdn);
-                const float s = sgn(clp - cln);
-                v = (1.f + s) * cn / 2.f + (1.f - s) * cp / 2.f;
-            }
-            const float chh = on_row ? (0.5f * m(0, -1) + 0.5f * m(0, 1)) - gdh : 0.f;
-            const float cvv = on_col ? (0.5f * m(-1, 0) + 0.5f * m(1, 0)) - gdv : 0.f;
-            out[ch] = ((v + chh) + cvv) + m(0, 0);
+        for (int tx = lane; tx < DM_PW; tx += 32) {
+            const int xx = min(max(X0 + tx - 3, 0), W2 - 1);
+            P[ty][tx] = __ldg(row + (long long)(xx & 1) * plane + (xx >> 1));
         }
-        const long long o = (long long)yy * W2 + xx;
-        yb[o] = out[0];
-        yb[(long long)H2 * W2 + o] = g;
-        yb[2LL * H2 * W2 + o] = out[1];
+    }
+    __syncthreads();
+
+    // ---- phase 2: the red / blue positions sit where (y ^ x) & 1 == (ry ^ rx); DM_GW / 2 of them per tile row
+    constexpr int rb = RY ^ RX;
+    for (int i = threadIdx.x; i < DM_GH * (DM_GW / 2); i += 256) {
+        const int gy = i / (DM_GW / 2), k = i - gy * (DM_GW / 2);
+        const int gx = 2 * k + (((Y0 + gy - 1) ^ (X0 - 1) ^ rb) & 1);          // X0, DM_GW even: parity of column gx
+        const int yy = Y0 + gy - 1, xx = X0 + gx - 1;
+        if (yy >= 0 && yy < H2 && xx >= 0 && xx < W2) G[gy][gx] = green_at<DM_PW>(&P[gy + 2][gx + 2]);
+    }
+    // halo positions outside the image (border tiles only): green of the clamped position, any colour
+    if (Y0 == 0 || X0 == 0 || Y0 + DM_TH >= H2 || X0 + DM_TW >= W2) {
+        for (int i = threadIdx.x; i < DM_GH * DM_GW; i += 256) {
+            const int gy = i / DM_GW, gx = i - gy * DM_GW;
+            const int yy = Y0 + gy - 1, xx = X0 + gx - 1;
+            if (yy >= 0 && yy < H2 && xx >= 0 && xx < W2) continue;
+            const int yc = min(max(yy, 0), H2 - 1), xc = min(max(xx, 0), W2 - 1);
+            const float *p = &P[yc - Y0 + 3][xc - X0 + 3];
+            G[gy][gx] = (((yc ^ xc) & 1) == rb) ? green_at<DM_PW>(p) : p[0];
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 3: cell (cy, cx) of the tile
+    const int cyy = Y0 + 2 * wrp, cxx = X0 + 2 * lane;
+    if (cyy >= H2 || cxx >= W2) return;
+    const bool up = cyy > 0, left = cxx > 0, down = cyy + 2 < H2, right = cxx + 2 < W2;     // neighbours outside the cell exist
+    float red[2][2], grn[2][2], blu[2][2];
+
+    // the pixel that carries colour A sees colour B on its four diagonals: B there from the diagonal colour differences
+    auto diag = [&](int py, int px, float &outB) {
+        const float *p = &P[2 * wrp + py + 3][2 * lane + px + 3];
+        const float *g = &G[2 * wrp + py + 1][2 * lane + px + 1];
+        const bool t = py ? true : up, bm = py ? down : true, l = px ? true : left, r = px ? right : true;
+        const float a00 = (t && l) ? p[-DM_PW - 1] : 0.f, a22 = (bm && r) ? p[DM_PW + 1] : 0.f;
+        const float a02 = (t && r) ? p[-DM_PW + 1] : 0.f, a20 = (bm && l) ? p[DM_PW - 1] : 0.f;
+        const float gc = g[0];
+        const float gdp = (g[-DM_GW - 1] + -2.f * gc) + g[DM_GW + 1], gdn = (g[-DM_GW + 1] + -2.f * gc) + g[DM_GW - 1];
+        const float cp = (0.5f * a00 + 0.5f * a22) - gdp / 4.f, cn = (0.5f * a02 + 0.5f * a20) - gdn / 4.f;
+        const float clp = fabsf(-a00 + a22) + fabsf(gdp), cln = fabsf(-a02 + a20) + fabsf(gdn);
+        const float s = sgn(clp - cln);
+        outB = (1.f + s) * cn / 2.f + (1.f - s) * cp / 2.f;
+        grn[py][px] = gc;
+    };
+    // a green pixel: the colour of its row from the horizontal neighbours, the colour of its column from the vertical ones
+    auto cross = [&](int py, int px, float &outRow, float &outCol) {
+        const float *p = &P[2 * wrp + py + 3][2 * lane + px + 3];
+        const float *g = &G[2 * wrp + py + 1][2 * lane + px + 1];
+        const bool t = py ? true : up, bm = py ? down : true, l = px ? true : left, r = px ? right : true;
+        const float gc = p[0];                                   // green sample of the CFA
+        // at the image border the replicated neighbour is this very pixel: its green is the sample itself
+        const float gl = l ? g[-1] : gc, grr = r ? g[1] : gc, gu = t ? g[-DM_GW] : gc, gd = bm ? g[DM_GW] : gc;
+        const float gdh = (0.25f * gl + -0.5f * gc) + 0.25f * grr;
+        const float gdv = (0.25f * gu + -0.5f * gc) + 0.25f * gd;
+        outRow = (0.5f * (l ? p[-1] : 0.f) + 0.5f * (r ? p[1] : 0.f)) - gdh;
+        outCol = (0.5f * (t ? p[-DM_PW] : 0.f) + 0.5f * (bm ? p[DM_PW] : 0.f)) - gdv;
+        grn[py][px] = gc;
+    };
+    // red pixel (ry, rx): blue from the diagonals; blue pixel (by, bx): red from the diagonals
+    red[RY][RX] = P[2 * wrp + RY + 3][2 * lane + RX + 3];
+    blu[BY][BX] = P[2 * wrp + BY + 3][2 * lane + BX + 3];
+    diag(RY, RX, blu[RY][RX]);
+    diag(BY, BX, red[BY][BX]);
+    // green on the red row (ry, bx): red along the row, blue along the column; green on the blue row (by, rx): the reverse
+    cross(RY, BX, red[RY][BX], blu[RY][BX]);
+    cross(BY, RX, blu[BY][RX], red[BY][RX]);
+
+    float *yb = a.y + (long long)blockIdx.z * 3 * H2 * W2 + (long long)cyy * W2 + cxx;
+    const long long pl = (long long)H2 * W2;
+#pragma unroll
+    for (int py = 0; py < 2; py++) {
+        *reinterpret_cast<float2 *>(yb + (long long)py * W2) = make_float2(red[py][0], red[py][1]);
+        *reinterpret_cast<float2 *>(yb + pl + (long long)py * W2) = make_float2(grn[py][0], grn[py][1]);
+        *reinterpret_cast<float2 *>(yb + 2 * pl + (long long)py * W2) = make_float2(blu[py][0], blu[py][1]);
     }
 }
 
@@ -126,9 +156,14 @@ cudaError_t launch_demosaic_ha(const float *x, float *y, int B, int H, int W, in
 {
     DemosaicArgs a;
     a.x = x; a.y = y; a.B = B; a.H = H; a.W = W;
-    a.ry = ry; a.rx = rx; a.by = by; a.bx = bx;
+    if (by != 1 - ry || bx != 1 - rx) return cudaErrorInvalidValue;        // red and blue sit on a diagonal of the cell
     const dim3 grid((2 * W + DM_TW - 1) / DM_TW, (2 * H + DM_TH - 1) / DM_TH, B);
-    demosaic_ha_kernel<<<grid, 256, 0, st>>>(a);
+    switch (ry * 2 + rx) {
+    case 0: demosaic_ha_kernel<0, 0><<<grid, 256, 0, st>>>(a); break;
+    case 1: demosaic_ha_kernel<0, 1><<<grid, 256, 0, st>>>(a); break;
+    case 2: demosaic_ha_kernel<1, 0><<<grid, 256, 0, st>>>(a); break;
+    default: demosaic_ha_kernel<1, 1><<<grid, 256, 0, st>>>(a); break;
+    }
     return cudaGetLastError();
 }
 

@@ -298,10 +298,98 @@ __global__ void __launch_bounds__(256) warp_tile_kernel(const WarpArgs a)
     }
 }
 
+// ------------------------------------------------------------------------------------------------ HWC, 4 channels
+//
+// single_warp / compute_flow_and_warp hand over frames in their on-disk layout: (H, W, 4) packed raw, channel
+// innermost (flow_utils.py:105-122, base_dataset.py:174-178).  There the 4 channels of a tap are ONE aligned 16-byte
+// load, so the gather needs no staging at all: 16 x LDG.128 per pixel through L1 (a warp's 32 pixels read 512
+// contiguous bytes per tap), one 128-bit store.  Same arithmetic as warp_kernel.
+template <int INTERP>
+__global__ void __launch_bounds__(256) warp_hwc4_kernel(const WarpArgs a)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int b = blockIdx.z;
+    if (x >= a.W || y >= a.H) return;
+    float fu, fv;
+    const float *fl = a.flow + (long long)b * 2 * a.fh * a.fw;
+    if (a.fh == a.H && a.fw == a.W) {
+        fu = fl[(long long)y * a.W + x];
+        fv = fl[(long long)a.H * a.W + (long long)y * a.W + x];
+    } else {
+        const float sy = a.H > 1 ? (float)(a.fh - 1) / (float)(a.H - 1) : 0.f;
+        const float sx = a.W > 1 ? (float)(a.fw - 1) / (float)(a.W - 1) : 0.f;
+        fu = up2_sample(fl, a.fh, a.fw, y, x, sy, sx);
+        fv = up2_sample(fl + (long long)a.fh * a.fw, a.fh, a.fw, y, x, sy, sx);
+    }
+    fu *= a.flow_mul;
+    fv *= a.flow_mul;
+    const float gxn = 2.0f * ((float)x + fu) / (float)(a.W - 1) - 1.0f;
+    const float gyn = 2.0f * ((float)y + fv) / (float)(a.H - 1) - 1.0f;
+    if (a.mask)
+        a.mask[((long long)b * a.H + y) * a.W + x] = (gxn >= -1.f && gxn <= 1.f && gyn >= -1.f && gyn <= 1.f) ? 1.f : 0.f;
+    float ix = ((gxn + 1.f) / 2.f) * (float)(a.W - 1);
+    float iy = ((gyn + 1.f) / 2.f) * (float)(a.H - 1);
+    const float4 *xb = reinterpret_cast<const float4 *>(a.x + (long long)b * a.xs_b);
+    const long long rowq = a.xs_h >> 2;                 // row pitch in float4 units
+    float4 acc;
+    if (INTERP == 1) {
+        const float fx0 = floorf(ix), fy0 = floorf(iy);
+        float cx[4], cy[4];
+        cubic_coeffs(ix - fx0, cx);
+        cubic_coeffs(iy - fy0, cy);
+        int ox[4];
+        long long oy[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            ox[k] = (int)fminf((float)(a.W - 1), fmaxf(fx0 - 1.f + (float)k, 0.f));
+            oy[k] = (long long)(int)fminf((float)(a.H - 1), fmaxf(fy0 - 1.f + (float)k, 0.f)) * rowq;
+        }
+        acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const float4 *q = xb + oy[r];
+            const float4 v0 = __ldg(q + ox[0]), v1 = __ldg(q + ox[1]), v2 = __ldg(q + ox[2]), v3 = __ldg(q + ox[3]);
+            acc.x += (v0.x * cx[0] + v1.x * cx[1] + v2.x * cx[2] + v3.x * cx[3]) * cy[r];
+            acc.y += (v0.y * cx[0] + v1.y * cx[1] + v2.y * cx[2] + v3.y * cx[3]) * cy[r];
+            acc.z += (v0.z * cx[0] + v1.z * cx[1] + v2.z * cx[2] + v3.z * cx[3]) * cy[r];
+            acc.w += (v0.w * cx[0] + v1.w * cx[1] + v2.w * cx[2] + v3.w * cx[3]) * cy[r];
+        }
+    } else {
+        ix = fminf((float)(a.W - 1), fmaxf(ix, 0.f));
+        iy = fminf((float)(a.H - 1), fmaxf(iy, 0.f));
+        const float fx0 = floorf(ix), fy0 = floorf(iy);
+        const int x0 = (int)fx0, y0 = (int)fy0;
+        const int x1 = min(x0 + 1, a.W - 1), y1 = min(y0 + 1, a.H - 1);
+        const float lx = ix - fx0, ly = iy - fy0;
+        const float wnw = (1.f - lx) * (1.f - ly), wne = lx * (1.f - ly), wsw = (1.f - lx) * ly, wse = lx * ly;
+        const float4 v00 = __ldg(xb + y0 * rowq + x0), v01 = __ldg(xb + y0 * rowq + x1);
+        const float4 v10 = __ldg(xb + y1 * rowq + x0), v11 = __ldg(xb + y1 * rowq + x1);
+        acc.x = v00.x * wnw + v01.x * wne + v10.x * wsw + v11.x * wse;
+        acc.y = v00.y * wnw + v01.y * wne + v10.y * wsw + v11.y * wse;
+        acc.z = v00.z * wnw + v01.z * wne + v10.z * wsw + v11.z * wse;
+        acc.w = v00.w * wnw + v01.w * wne + v10.w * wsw + v11.w * wse;
+    }
+    float *ob = a.out + (long long)b * a.os_b + (long long)y * a.os_h + (long long)x * a.os_w;
+    if (a.os_c == 1 && ((reinterpret_cast<uintptr_t>(ob) & 15) == 0)) {
+        *reinterpret_cast<float4 *>(ob) = acc;
+    } else {
+        ob[0] = acc.x; ob[a.os_c] = acc.y; ob[2 * a.os_c] = acc.z; ob[3 * a.os_c] = acc.w;
+    }
+}
+
 cudaError_t launch_warp(const WarpArgs &a, cudaStream_t st)
 {
     if (a.B <= 0 || a.C <= 0 || a.H <= 0 || a.W <= 0) return cudaSuccess;
     dim3 grid((a.W + 31) / 32, (a.H + 7) / 8, a.B);
+    if (a.C == 4 && a.xs_c == 1 && a.xs_w == 4 && (a.xs_h & 3) == 0 && (a.xs_b & 3) == 0 &&
+        (reinterpret_cast<uintptr_t>(a.x) & 15) == 0) {   // channel-innermost 4-channel frames: 128-bit gathers
+        if (a.interp == 1)
+            warp_hwc4_kernel<1><<<grid, 256, 0, st>>>(a);
+        else
+            warp_hwc4_kernel<0><<<grid, 256, 0, st>>>(a);
+        return cudaGetLastError();
+    }
     if (a.xs_w == 1 && a.C >= 3) {                      // plane-contiguous input: staged gathers
         if (a.interp == 1)
             warp_tile_kernel<1><<<grid, 256, 0, st>>>(a);

@@ -219,6 +219,8 @@ def main(argv=None):
     args = ap.parse_args(argv)
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+    from . import hostbind
+    hostbind.bind_to_gpu(int(os.environ.get("LOCAL_RANK", 0)))     # pinned staging buffers on the GPU's NUMA node
     if world > 1:
         dist.init_process_group("gloo")
     files = precompute_dataset(list_videos(args.noisy), args.flow, args.warped, args.patch_depth, args.future_patch_depth,

@@ -356,3 +356,28 @@ def test_demosaic_against_oracle_sizes(bridge, H, W, pattern):
     assert np.array_equal(gray, want)
     if pattern == "gbrg":     # the CFA samples survive demosaic -> remosaick untouched
         assert np.array_equal(demosaic_ref.remosaick(y, pattern), x.numpy())
+
+
+@pytest.mark.parametrize("interp", ["bicubic", "bilinear"])
+def test_warp_channel_innermost_frames(bridge, interp):
+    """Frames in their on-disk (H, W, 4) layout, viewed as [B, 4, H, W] (single_warp, flow_utils.py:105-122): the
+    128-bit gather kernel, with a half-resolution flow, a mask, and both channel-innermost and plane outputs."""
+    from rvdd_release_b200 import flow_utils
+    g = torch.Generator().manual_seed(11)
+    B, H, W = 3, 70, 102
+    hwc = torch.randn(B, H, W, 4, generator=g)
+    x = hwc.permute(0, 3, 1, 2)                                   # strides (H*W*4, 1, W*4, 4)
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    flow = torch.stack((3.0 * torch.sin(yy / 9.0) + 0.3 * torch.randn(H, W, generator=g),
+                        -2.0 + 4.0 * torch.cos(xx / 13.0)), 0)[None].repeat(B, 1, 1, 1).contiguous()
+    flow[1] += 60.0                                               # one image sampled far outside
+    ref, mref = warp_ref.warp(x.contiguous(), flow, interp)
+    y, m = flow_utils.warp(x.cuda(), flow.cuda(), interp)
+    assert rel_err(y.cpu().numpy(), ref.numpy()) <= WARP_RTOL and np.array_equal(m.cpu().numpy(), mref.numpy())
+    out_hwc = torch.empty(B, H, W, 4, device="cuda")
+    bridge.warp(x.cuda(), flow.cuda(), interp, want_mask=False, out=out_hwc.permute(0, 3, 1, 2))
+    assert torch.equal(out_hwc.permute(0, 3, 1, 2), y)
+    half = (0.5 * flow[:, :, ::2, ::2]).contiguous()
+    rh, _ = warp_ref.warp(x.contiguous(), warp_ref.upsample_factor_2(half, 2), interp)
+    yh, _ = flow_utils.warp(x.cuda(), half.cuda(), interp, flow_mul=2.0)
+    assert rel_err(yh.cpu().numpy(), rh.numpy()) <= 5 * WARP_RTOL

@@ -287,8 +287,12 @@ __device__ __forceinline__ double iterate_strip_tma(const SolverArgs &SA, int gr
     refill(0);
 
     int y = y0, i = 0;                                   // i = y - y0
+    // One copy of the row body; the row state is moved from B to A after every row.  Unrolling by two (the states
+    // swapping roles) saves the 32 moves but doubles the hot loop's code, and measured 1.3 % slower (instruction
+    // cache: stall_no_inst 6 %).
+#pragma unroll 1
     while (true) {
-        bool down = (i + 1 < nr);
+        const bool down = (i + 1 < nr);
         if (down) {
             tma_eval_row(T, lane, E, false, y + 2 == ny, K, A.p12, A.p22, B, status);
             refill(i + 1);
@@ -296,14 +300,7 @@ __device__ __forceinline__ double iterate_strip_tma(const SolverArgs &SA, int gr
         finish_row<4>(P, row, E, down, K, A, B, err, active);
         row += nx; ++i;
         if (++y >= y1) break;
-        down = (i + 1 < nr);
-        if (down) {
-            tma_eval_row(T, lane, E, false, y + 2 == ny, K, B.p12, B.p22, A, status);
-            refill(i + 1);
-        }
-        finish_row<4>(P, row, E, down, K, B, A, err, active);
-        row += nx; ++i;
-        if (++y >= y1) break;
+        A = B;
     }
     return err;
 }

@@ -36,4 +36,4 @@ for r in data:
     ops[o] = ops.get(o, 0) + int(r[ix["Instructions Executed"]])
 S = sum(ops.values())
 print("# executed warp-instructions by opcode:", ", ".join("%s %.1f%%" % (k, 100 * v / S) for k, v in sorted(ops.items(), key=lambda kv: -kv[1])[:14]))
-print("# TMA / mbarrier SASS present:", ", ".join(k for k in ("UBLKCP", "SYNCS", "ELECT") if k in ops))
+print("# TMA / mbarrier SASS present:", ", ".join(k for k in ("UTMALDG", "UBLKCP", "SYNCS", "ELECT") if k in ops))

@@ -17,7 +17,7 @@ import torch.nn.functional as F
 def warp(x, flow, interp="bicubic"):
     """x [B,C,H,W], flow [B,2,H,W] (ch0 = x-displacement) -> (warped, mask [B,1,H,W] float)."""
     B, C, H, W = x.shape
-    ys, xs = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    ys, xs = torch.meshgrid(torch.arange(H, device=x.device), torch.arange(W, device=x.device), indexing="ij")
     base = torch.stack((xs, ys), 0).unsqueeze(0).float()                 # flow_utils.py:84-89
     v = base + flow                                                       # :90
     gx = 2.0 * v[:, 0] / (W - 1) - 1.0                                    # :93

@@ -69,3 +69,68 @@ def test_recurrent_convunet_psnr_within_0p02_db(bridge, fixture, fused_upsample,
     assert np.max(np.abs(np.array(psnrs) - ref)) <= 0.02, (psnrs, ref.tolist())
     # much tighter than the PSNR gate: the last denoised frame itself (cuDNN vs CPU convolutions included)
     assert float((den[0].cpu() - torch.from_numpy(d["denoised_last"])).abs().max()) <= 2e-3
+
+
+def test_recurrent_convunet_feat_future_psnr_within_0p02_db(bridge):
+    """Config 3 (scripts/test-recurrent-feat-future-convunet.sh): per frame two flows (t-1 -> t, t+1 -> t), the warp of
+    the previous denoised frame, of its 48-channel feature map and of the next noisy frame (recurrent_model.py:281-324).
+    All flows come out of ONE batched solver call; the three warps write straight into the network's input buffers
+    (half-resolution flow, x2 upsampling fused), the demosaic is csrc/demosaic.cu."""
+    from rvdd_release_b200.hamilton_adam import HamiltonAdam
+    d = np.load(os.path.join(GOLDEN, "pipeline_convunet_feat_future_iso12800.npz"))
+    net = torch.jit.load(os.path.join(GOLDEN, "pipeline_convunet_feat_future_iso12800_denoiser.pt"), map_location="cuda").eval()
+    nfr, h, w = (int(v) for v in d["geometry"])
+    seq = synth.sequence(nfr, h, w, "iso12800")
+    assert float(seq.numpy().astype(np.float64).sum()) == float(d["frames_checksum"]), "synthetic input drifted"
+    frames = seq.cuda()
+    gt = torch.from_numpy(d["gt"].astype(np.float32)).cuda()[:, None].repeat(1, 3, 1, 1)
+
+    T = nfr - 2                                                    # frames 1 .. nfr-2 have a past and a future
+    src = list(range(0, T)) + list(range(2, T + 2))                # past sources t-1, future sources t+1
+    tgt = list(range(1, T + 1)) * 2
+    flows = bridge.tvl1_flow(bridge.gray(frames), src=src, tgt=tgt, check=True)
+    assert torch.equal(flows[:T].cpu(), torch.from_numpy(d["flows"]).permute(0, 3, 1, 2)), "past flows differ"
+    assert torch.equal(flows[T:].cpu(), torch.from_numpy(d["future_flows"]).permute(0, 3, 1, 2)), "future flows differ"
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ha = HamiltonAdam("gbrg")
+    from oracle import warp_ref
+
+    def run(ours):
+        """ours=True: csrc warps writing into the network's buffers; False: the reference's grid_sample warp on the GPU
+        (oracle/warp_ref.py on CUDA tensors) -- same cuDNN denoiser, so the difference isolates the alignment path."""
+        lastden = n[0:1]
+        lastfeat = torch.zeros(1, 48, 2 * h, 2 * w, device="cuda")
+        netinput = torch.empty(1, 9, 2 * h, 2 * w, device="cuda")
+        featinput = torch.empty_like(lastfeat)
+        psnrs, den = [], None
+        for t in range(1, T + 1):
+            if ours:
+                bridge.warp(lastden, flows[t - 1:t], "bicubic", flow_mul=2.0, want_mask=False, out=netinput[:, 0:3])
+                bridge.warp(n[t + 1:t + 2], flows[T + t - 1:T + t], "bicubic", flow_mul=2.0, want_mask=False, out=netinput[:, 6:9])
+                bridge.warp(lastfeat, flows[t - 1:t], "bicubic", flow_mul=2.0, want_mask=False, out=featinput)
+            else:
+                up, fup = warp_ref.upsample_factor_2(flows[t - 1:t], 2), warp_ref.upsample_factor_2(flows[T + t - 1:T + t], 2)
+                netinput[:, 0:3] = warp_ref.warp(lastden, up, "bicubic")[0]
+                netinput[:, 6:9] = warp_ref.warp(n[t + 1:t + 2], fup, "bicubic")[0]
+                featinput = warp_ref.warp(lastfeat, up, "bicubic")[0]
+            netinput[:, 3:6] = n[t]
+            den, feat = net(netinput, featinput)
+            lastden, lastfeat = den.clone(), feat.clone()
+            psnrs.append(_psnr(den, gt[t:t + 1]))
+        return np.array(psnrs), den[0].cpu()
+
+    with torch.no_grad():
+        n = ha((2.0 * (frames / 4095.0) - 1.0).permute(0, 3, 1, 2).contiguous())          # [nfr, 3, 2h, 2w] in one launch
+        psnr_ours, den_ours = run(True)
+        psnr_gref, den_gref = run(False)
+    ref, golden = d["psnr"], torch.from_numpy(d["denoised_last"])
+    assert np.max(np.abs(psnr_ours - ref)) <= 0.02, (psnr_ours.tolist(), ref.tolist())
+    # The recurrence (denoised frame AND 48 feature channels fed back for four frames, ISO 12800 noise) amplifies every
+    # last-bit difference: the same loop with the reference's own warp on the GPU already sits ~3e-3 from the CPU run
+    # (cuDNN vs CPU convolutions).  Our alignment path must not add to that.
+    noise = float((den_gref - golden).abs().max())
+    assert float((den_ours - golden).abs().max()) <= max(2e-3, 2.0 * noise), (float((den_ours - golden).abs().max()), noise)
+    assert float((den_ours - den_gref).abs().max()) <= max(2e-3, 2.0 * noise)
+    assert np.max(np.abs(psnr_ours - psnr_gref)) <= 0.01

@@ -82,27 +82,41 @@ def test_warp_ref_matches_reference_golden(path):
     assert np.abs(man - g["bicubic"][0]).max() < 2e-4 * max(1.0, np.abs(g["bicubic"]).max())
 
 
-def test_oracle_reproduces_reference_pipeline_psnr(port):
-    """The end-to-end fixture (tests/golden/make_pipeline_golden.py: reference flows, reference warp, shipped
-    recurrent-convunet-iso3200 checkpoint) replayed on the CPU with the ORACLE's flow and warp in the loop: same flows
-    bit for bit, same PSNR per frame.  The GPU test (test_gpu_pipeline.py) runs the same loop with the CUDA path."""
-    d = np.load(os.path.join(GOLDEN, "pipeline_convunet_iso3200.npz"))
-    net = torch.jit.load(os.path.join(GOLDEN, "pipeline_convunet_iso3200_denoiser.pt"), map_location="cpu").eval()
-    ha = torch.jit.load(os.path.join(GOLDEN, "pipeline_hamilton_adams_gbrg_48x80.pt"), map_location="cpu").eval()
+@pytest.mark.parametrize("name,iso,feat_future", [("pipeline_convunet_iso3200", "iso3200", False),
+                                                  ("pipeline_convunet_feat_future_iso12800", "iso12800", True)])
+def test_oracle_reproduces_reference_pipeline_psnr(port, name, iso, feat_future):
+    """The end-to-end fixtures (tests/golden/make_pipeline_golden.py: reference flows, reference demosaic and warp,
+    shipped recurrent-convunet checkpoints, with and without feature recurrence + future frame) replayed on the CPU
+    with the ORACLE's flow, warp and demosaic in the loop: same flows bit for bit, same PSNR per frame.  The GPU tests
+    (test_gpu_pipeline.py) run the same loops with the CUDA path."""
+    from oracle import demosaic_ref
+    d = np.load(os.path.join(GOLDEN, name + ".npz"))
+    net = torch.jit.load(os.path.join(GOLDEN, name + "_denoiser.pt"), map_location="cpu").eval()
     nfr, h, w = (int(v) for v in d["geometry"])
-    seq = synth.sequence(nfr, h, w, "iso3200")
+    seq = synth.sequence(nfr, h, w, iso)
     assert float(seq.numpy().astype(np.float64).sum()) == float(d["frames_checksum"])
     g = np.mean(seq.numpy(), axis=3)
     gt = torch.from_numpy(d["gt"].astype(np.float32))[:, None].repeat(1, 3, 1, 1)
+
+    def up_flow(tgt, src, want):
+        flow = port.tvl1flow(g[tgt], g[src])
+        assert np.array_equal(flow.transpose(1, 2, 0), want)
+        return warp_ref.upsample_factor_2(torch.from_numpy(flow[None]), 2)
+
     with torch.no_grad():
-        n = [ha((2.0 * (seq[t] / 4095.0) - 1.0).permute(2, 0, 1)[None].contiguous()) for t in range(nfr)]
+        n = [torch.from_numpy(demosaic_ref.hamilton_adam((2.0 * (seq[t] / 4095.0) - 1.0).permute(2, 0, 1)[None].numpy()))
+             for t in range(nfr)]
         lastden, psnrs = n[0], []
-        for t in range(1, nfr):
-            flow = port.tvl1flow(g[t], g[t - 1])
-            assert np.array_equal(flow.transpose(1, 2, 0), d["flows"][t - 1])
-            up = warp_ref.upsample_factor_2(torch.from_numpy(flow[None]), 2)
-            warped, _ = warp_ref.warp(lastden, up, "bicubic")
-            den = net(torch.cat((warped, n[t]), 1))
+        lastfeat = torch.zeros(1, 48, 2 * h, 2 * w)
+        for t in range(1, nfr - 1 if feat_future else nfr):
+            up = up_flow(t, t - 1, d["flows"][t - 1])
+            netinput = torch.cat((warp_ref.warp(lastden, up, "bicubic")[0], n[t]), 1)
+            if feat_future:
+                fup = up_flow(t, t + 1, d["future_flows"][t - 1])
+                netinput = torch.cat((netinput, warp_ref.warp(n[t + 1], fup, "bicubic")[0]), 1)
+                den, lastfeat = net(netinput, warp_ref.warp(lastfeat, up, "bicubic")[0])
+            else:
+                den = net(netinput)
             lastden = den.clone()
             psnrs.append(float(10 * torch.log10(4.0 / torch.mean((den - gt[t:t + 1]) ** 2))))
     assert np.max(np.abs(np.array(psnrs) - d["psnr"])) <= 1e-3

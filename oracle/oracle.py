@@ -72,6 +72,7 @@ class PortLib:
         L.port_solve_scale.argtypes = [_f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.POINTER(PortParams),
                                        C.c_int, C.c_void_p]
         L.port_default_params.argtypes = [C.POINTER(PortParams)]
+        L.port_multiscale.argtypes = [_f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.POINTER(PortParams), C.c_void_p]
 
     def nscales(self, nx, ny, zfactor=0.5, req=100):
         return self.L.port_clamp_nscales(nx, ny, zfactor, req)
@@ -86,6 +87,20 @@ class PortLib:
         ny, nx = I0.shape
         u = np.zeros((2, ny, nx), np.float32)
         self.L.port_tvl1flow(_c(I0), _c(I1), u, nx, ny)
+        return u
+
+    def multiscale(self, I0, I1, tau=0.25, lam=0.15, theta=0.3, nscales=100, fscale=0, zfactor=0.5, nwarps=5, epsilon=0.01):
+        """Dual_TVL1_optic_flow_multiscale (tvl1flow_lib.c:343-472) with explicit parameters; nscales is clamped the
+        way libBridge.cpp:131-138 clamps it."""
+        ny, nx = I0.shape
+        P = PortParams()
+        self.L.port_default_params(C.byref(P))
+        P.tau, P.lambda_, P.theta, P.fscale, P.zfactor, P.nwarps, P.epsilon = tau, lam, theta, fscale, zfactor, nwarps, epsilon
+        P.nscales = self.L.port_clamp_nscales(nx, ny, zfactor, nscales)
+        if P.nscales < P.fscale:
+            P.fscale = P.nscales
+        u = np.zeros((2, ny, nx), np.float32)
+        self.L.port_multiscale(_c(I0), _c(I1), u[0], u[1], nx, ny, C.byref(P), None)
         return u
 
     def tvl1flow_traced(self, I0, I1, err_mode=0, err_cap=0):
@@ -200,6 +215,21 @@ class RefLib:
         ny, nx = I0.shape
         u = np.zeros((2, ny, nx), np.float32)
         self.L.tvl1flow(_c(I0), _c(I1), u, nx, ny)
+        return u
+
+    def multiscale(self, I0, I1, tau=0.25, lam=0.15, theta=0.3, nscales=100, fscale=0, zfactor=0.5, nwarps=5, epsilon=0.01):
+        """The reference's Dual_TVL1_optic_flow_multiscale itself (tvl1flow_lib.c:343), nscales clamped by the caller
+        exactly as libBridge.cpp:131-138 does."""
+        import math
+        ny, nx = I0.shape
+        N = np.float32(1 + math.log(math.hypot(nx, ny) / 16.0) / math.log(1 / float(np.float32(zfactor))))
+        if N < nscales:
+            nscales = int(N)
+        if nscales < fscale:
+            fscale = nscales
+        u = np.zeros((2, ny, nx), np.float32)
+        self.L.Dual_TVL1_optic_flow_multiscale(_c(I0), _c(I1), u[0], u[1], nx, ny, tau, lam, theta, nscales, fscale, zfactor,
+                                               nwarps, epsilon, False)
         return u
 
     def solve_scale(self, I0, I1, u1, u2, tau=0.25, lam=0.15, theta=0.3, warps=5, eps=0.01):

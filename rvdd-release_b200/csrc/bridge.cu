@@ -351,6 +351,12 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
     CK(launch_minmax(dtab, dtab + K, nx * ny, K, slots, st));
     CK(launch_gauss(dtab, nullptr, 0, pyr, P.total, nx, ny, 2 * K, pre, slots, K, st));
     for (int s = 1; s < S; s++) {
+        if (p.zfactor == 0.5f) {      // the default: blur + pick of the even pixels fused, no full-size temporary
+            const cudaError_t e = launch_gauss_decimate(pyr + P.off[s - 1], P.total, pyr + P.off[s], P.total, P.nx[s - 1],
+                                                        P.ny[s - 1], P.nx[s], P.ny[s], 2 * K, zoom, st);
+            if (e == cudaSuccess) continue;
+            if (e != cudaErrorNotSupported) return fail("launch_gauss_decimate", e);
+        }
         CK(launch_gauss(nullptr, pyr + P.off[s - 1], P.total, tmp, plane, P.nx[s - 1], P.ny[s - 1], 2 * K, zoom, nullptr, K, st));
         CK(launch_resample(tmp, plane, P.nx[s - 1], P.ny[s - 1], pyr + P.off[s], P.total, P.nx[s], P.ny[s], p.zfactor,
                            p.zfactor, 2 * K, st));

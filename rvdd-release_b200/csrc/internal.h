@@ -57,6 +57,8 @@ cudaError_t launch_minmax(const float *const *I0, const float *const *I1, int n,
 cudaError_t launch_gauss(const float *const *srcs, const float *src_base, long long src_stride, float *dst_base,
                          long long dst_stride, int nx, int ny, int nimg, const GaussTaps &taps, const int *slots,
                          int npairs, cudaStream_t st);
+cudaError_t launch_gauss_decimate(const float *src_base, long long src_stride, float *dst_base, long long dst_stride, int nx,
+                                  int ny, int nxx, int nyy, int nimg, const GaussTaps &taps, cudaStream_t st);
 cudaError_t launch_resample(const float *src_base, long long src_stride, int nx, int ny, float *dst_base,
                             long long dst_stride, int nxx, int nyy, float fx, float fy, int nimg, cudaStream_t st);
 cudaError_t launch_gray(const float *img, float *gray, long long npix_total, int c, cudaStream_t st);

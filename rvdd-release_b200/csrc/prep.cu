@@ -100,22 +100,36 @@ cudaError_t launch_minmax(const float *const *I0, const float *const *I1, int n,
 #define GT_X 64
 #define GT_Y 32
 
-template <bool NORM>
+// The reference accumulates in double (mask.c:279-285, :319-325); float -> double conversions run at a quarter of the
+// FP64 rate on this GPU (16 / clk / SM), and a tap-by-tap conversion made them the kernel's bottleneck.  So every pixel
+// is converted ONCE when the tile is staged, the row pass reads doubles, and its result -- rounded to float as the
+// reference's in-place store does -- is converted back once for the column pass.
+//
+// DEC == false: dst = gaussian(src), same size.
+// DEC == true : zoom_out with factor 0.5 (zoom.c:41-77): the bicubic sample of the blurred image at (2 x, 2 y) has zero
+//               fractions and is the blurred pixel itself (bicubic_interpolation.c:100-108 with x = 0), so only the even
+//               columns need the row pass and only the even rows / columns the column pass, and the quarter-size level
+//               is written directly: dst is (nxx, nyy), the tile covers 2 GT_X x 2 GT_Y input pixels.
+template <bool NORM, bool DEC, int RR>
 __global__ void __launch_bounds__(256)
 gauss_tile_kernel(const float *const *__restrict__ srcs, const float *__restrict__ src_base, long long src_stride,
-                  float *__restrict__ dst_base, long long dst_stride, int nx, int ny, GaussTaps taps,
+                  float *__restrict__ dst_base, long long dst_stride, int nx, int ny, int nxx, int nyy, GaussTaps taps,
                   const int *__restrict__ slots, int npairs)
 {
-    extern __shared__ float smem[];
+    extern __shared__ double smem_d[];
+    constexpr int STEP = DEC ? 2 : 1;
+    constexpr int TY = DEC ? GT_Y / 2 : GT_Y;      // output rows per tile (the decimating tile stages 2 TY + 2R input rows)
     const int z = blockIdx.z;
     const float *src = srcs ? srcs[z] : src_base + (long long)z * src_stride;
     float *dst = dst_base + (long long)z * dst_stride;
-    const int R = taps.size - 1;
-    const int in_w = GT_X + 2 * R, in_h = GT_Y + 2 * R;
-    float *s_in = smem;                      // [in_h][in_w]
-    float *s_row = smem + in_h * in_w;       // [in_h][GT_X]
-    const int ox = blockIdx.x * GT_X, oy = blockIdx.y * GT_Y;
-    const int tid = threadIdx.x;
+    constexpr int R = RR;                    // taps.size - 1 (mask.c:225), compile-time so the sliding windows stay in registers
+    constexpr int GB = 4;                    // outputs per thread and pass
+    constexpr int in_w = STEP * GT_X + 2 * R, in_h = STEP * TY + 2 * R;
+    constexpr int in_p = in_w | 1;           // odd pitch: lanes walking down a column of doubles hit distinct banks
+    double *s_in = smem_d;                   // [in_h][in_p]
+    double *s_row = smem_d + in_h * in_p;    // [in_h][GT_X]   (row-pass results at the columns the outputs need)
+    const int ox = blockIdx.x * GT_X * STEP, oy = blockIdx.y * TY * STEP;        // tile origin in the input
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
 
     float lo = 0.f, den = 0.f;
     if (NORM) {
@@ -123,54 +137,109 @@ gauss_tile_kernel(const float *const *__restrict__ srcs, const float *__restrict
         lo = ord2f(slots[2 * k]);
         den = FSUB(ord2f(slots[2 * k + 1]), lo);
     }
-    for (int i = tid; i < in_h * in_w; i += 256) {
-        const int r = i / in_w, c = i - r * in_w;
-        const int gy = rvdd_reflect(oy - R + r, ny), gx = rvdd_reflect(ox - R + c, nx);
-        float v = src[(long long)gy * nx + gx];
-        if (NORM && den > 0.f) v = rvdd_normalize_px(v, lo, den);
-        s_in[i] = v;
+    for (int r = wrp; r < in_h; r += 8) {
+        const int gy = rvdd_reflect(oy - R + r, ny);
+        const float *srow = src + (long long)gy * nx;
+        for (int c = lane; c < in_w; c += 32) {
+            float v = __ldg(srow + rvdd_reflect(ox - R + c, nx));
+            if (NORM && den > 0.f) v = rvdd_normalize_px(v, lo, den);
+            s_in[r * in_p + c] = (double)v;
+        }
     }
     __syncthreads();
-    // rows (mask.c:279-285): B[0]*R[i] + sum_j B[j]*(R[i-j]+R[i+j]) in double, stored as float
-    for (int i = tid; i < in_h * GT_X; i += 256) {
-        const int r = i / GT_X, c = i - r * GT_X;
-        const float *row = s_in + r * in_w + c + R;
-        double acc = DMUL(taps.B[0], (double)row[0]);
-        for (int j = 1; j <= R; j++) acc = DADD(acc, DMUL(taps.B[j], DADD((double)row[-j], (double)row[j])));
-        s_row[i] = (float)acc;
+    // rows (mask.c:279-285): B[0]*R[i] + sum_j B[j]*(R[i-j]+R[i+j]) in double, stored as float.  A thread owns a run of
+    // GB consecutive output columns of one row and slides over the 2R + STEP (GB - 1) + 1 inputs it needs (3x fewer
+    // shared-memory reads than output by output); lanes map to rows, the odd row pitch keeps that conflict-free.
+    for (int i = threadIdx.x; i < in_h * (GT_X / GB); i += 256) {
+        const int r = i % in_h, c0 = (i / in_h) * GB;
+        const double *row = s_in + r * in_p + STEP * c0;
+        double w[2 * RR + STEP * (GB - 1) + 1];
+#pragma unroll
+        for (int k = 0; k < 2 * RR + STEP * (GB - 1) + 1; k++) w[k] = row[k];
+#pragma unroll
+        for (int o = 0; o < GB; o++) {
+            double acc = DMUL(taps.B[0], w[STEP * o + RR]);
+#pragma unroll
+            for (int j = 1; j <= RR; j++) acc = DADD(acc, DMUL(taps.B[j], DADD(w[STEP * o + RR - j], w[STEP * o + RR + j])));
+            s_row[r * GT_X + c0 + o] = (double)(float)acc;
+        }
     }
     __syncthreads();
-    // columns (mask.c:319-325)
-    for (int i = tid; i < GT_Y * GT_X; i += 256) {
-        const int r = i / GT_X, c = i - r * GT_X;
-        if (oy + r >= ny || ox + c >= nx) continue;
-        const float *col = s_row + (r + R) * GT_X + c;
-        double acc = DMUL(taps.B[0], (double)col[0]);
-        for (int j = 1; j <= R; j++)
-            acc = DADD(acc, DMUL(taps.B[j], DADD((double)col[-j * GT_X], (double)col[j * GT_X])));
-        dst[(long long)(oy + r) * nx + ox + c] = (float)acc;
+    // columns (mask.c:319-325): a thread owns GB consecutive output rows of one column, lanes map to columns
+    const int onx = DEC ? nxx : nx, ony = DEC ? nyy : ny;
+    const int qx = blockIdx.x * GT_X, qy = blockIdx.y * TY;                      // tile origin in the output
+    for (int i = threadIdx.x; i < (TY / GB) * GT_X; i += 256) {
+        const int c = i % GT_X, r0 = (i / GT_X) * GB;
+        const double *col = s_row + (STEP * r0) * GT_X + c;
+        double w[2 * RR + STEP * (GB - 1) + 1];
+#pragma unroll
+        for (int k = 0; k < 2 * RR + STEP * (GB - 1) + 1; k++) w[k] = col[k * GT_X];
+#pragma unroll
+        for (int o = 0; o < GB; o++) {
+            double acc = DMUL(taps.B[0], w[STEP * o + RR]);
+#pragma unroll
+            for (int j = 1; j <= RR; j++) acc = DADD(acc, DMUL(taps.B[j], DADD(w[STEP * o + RR - j], w[STEP * o + RR + j])));
+            if (qy + r0 + o < ony && qx + c < onx) dst[(long long)(qy + r0 + o) * onx + qx + c] = (float)acc;
+        }
     }
 }
 
+static size_t gauss_smem(int R, int step)
+{
+    const int ty = step == 2 ? GT_Y / 2 : GT_Y;
+    return sizeof(double) * ((size_t)(step * ty + 2 * R) * ((step * GT_X + 2 * R) | 1) + (size_t)(step * ty + 2 * R) * GT_X);
+}
+
+template <bool NORM, bool DEC, int RR, typename... Args>
+static cudaError_t gauss_go(dim3 grid, size_t smem, cudaStream_t st, Args... args)
+{
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(gauss_tile_kernel<NORM, DEC, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr = true;
+    }
+    gauss_tile_kernel<NORM, DEC, RR><<<grid, 256, smem, st>>>(args...);
+    return cudaGetLastError();
+}
+
+// The sliding windows need the tap radius R = taps.size - 1 (mask.c:225) at compile time.  The normalising variant is
+// only ever used with the presmoothing kernel (sigma 0.8: R = 4), the decimating one with zoom factor 0.5 (sigma 1.04:
+// R = 5); the plain variant is instantiated for R = 1 .. 12, which covers zoom factors down to 0.24; anything wider is
+// refused (cudaErrorNotSupported -> "kernel too wide").
+#define GAUSS_CASE(NORM, DEC, R, ...) case R: return gauss_go<NORM, DEC, R>(__VA_ARGS__);
 cudaError_t launch_gauss(const float *const *srcs, const float *src_base, long long src_stride, float *dst_base,
                          long long dst_stride, int nx, int ny, int nimg, const GaussTaps &taps, const int *slots,
                          int npairs, cudaStream_t st)
 {
     const int R = taps.size - 1;
-    const size_t smem = sizeof(float) * ((size_t)(GT_Y + 2 * R) * (GT_X + 2 * R) + (size_t)(GT_Y + 2 * R) * GT_X);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(gauss_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(gauss_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        attr_done = true;
+    const size_t smem = gauss_smem(R, 1);
+    if (smem > 200 * 1024) return cudaErrorNotSupported;
+    const dim3 grid((nx + GT_X - 1) / GT_X, (ny + GT_Y - 1) / GT_Y, nimg);
+#define ARGS grid, smem, st, srcs, src_base, src_stride, dst_base, dst_stride, nx, ny, nx, ny, taps, slots, npairs
+    if (slots) return R == 4 ? gauss_go<true, false, 4>(ARGS) : cudaErrorNotSupported;
+    switch (R) {
+        GAUSS_CASE(false, false, 1, ARGS) GAUSS_CASE(false, false, 2, ARGS) GAUSS_CASE(false, false, 3, ARGS)
+        GAUSS_CASE(false, false, 4, ARGS) GAUSS_CASE(false, false, 5, ARGS) GAUSS_CASE(false, false, 6, ARGS)
+        GAUSS_CASE(false, false, 7, ARGS) GAUSS_CASE(false, false, 8, ARGS) GAUSS_CASE(false, false, 9, ARGS)
+        GAUSS_CASE(false, false, 10, ARGS) GAUSS_CASE(false, false, 11, ARGS) GAUSS_CASE(false, false, 12, ARGS)
+    default: return cudaErrorNotSupported;
     }
-    if (smem > 160 * 1024) return cudaErrorInvalidValue;
-    dim3 grid((nx + GT_X - 1) / GT_X, (ny + GT_Y - 1) / GT_Y, nimg);
-    if (slots)
-        gauss_tile_kernel<true><<<grid, 256, smem, st>>>(srcs, src_base, src_stride, dst_base, dst_stride, nx, ny, taps, slots, npairs);
-    else
-        gauss_tile_kernel<false><<<grid, 256, smem, st>>>(srcs, src_base, src_stride, dst_base, dst_stride, nx, ny, taps, slots, npairs);
-    return cudaGetLastError();
+#undef ARGS
+}
+
+// zoom_out with factor exactly 0.5: Gaussian + pick of the even pixels in one pass; returns cudaErrorNotSupported when the
+// tile does not fit in shared memory (the caller then uses launch_gauss + launch_resample).
+cudaError_t launch_gauss_decimate(const float *src_base, long long src_stride, float *dst_base, long long dst_stride, int nx,
+                                  int ny, int nxx, int nyy, int nimg, const GaussTaps &taps, cudaStream_t st)
+{
+    const int R = taps.size - 1;
+    const size_t smem = gauss_smem(R, 2);
+    if (smem > 200 * 1024) return cudaErrorNotSupported;
+    const dim3 grid((nxx + GT_X - 1) / GT_X, (nyy + GT_Y / 2 - 1) / (GT_Y / 2), nimg);
+    const float *const *nosrcs = nullptr;
+    const int *noslots = nullptr;
+    if (R != 5) return cudaErrorNotSupported;
+    return gauss_go<false, true, 5>(grid, smem, st, nosrcs, src_base, src_stride, dst_base, dst_stride, nx, ny, nxx, nyy, taps, noslots, 1);
 }
 
 // ------------------------------------------------------------------------------------------------ resample

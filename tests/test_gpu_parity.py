@@ -381,3 +381,23 @@ def test_warp_channel_innermost_frames(bridge, interp):
     rh, _ = warp_ref.warp(x.contiguous(), warp_ref.upsample_factor_2(half, 2), interp)
     yh, _ = flow_utils.warp(x.cuda(), half.cuda(), interp, flow_mul=2.0)
     assert rel_err(yh.cpu().numpy(), rh.numpy()) <= 5 * WARP_RTOL
+
+
+@pytest.mark.parametrize("kw", [dict(zfactor=0.7, nwarps=3, tau=0.2, lam=0.1, theta=0.25, epsilon=0.02),
+                                dict(zfactor=0.5, nwarps=2, nscales=3, lam=0.3, theta=0.4, epsilon=0.005),
+                                dict(zfactor=0.35, nwarps=4, fscale=1),
+                                dict(zfactor=0.8, nscales=4, nwarps=1)])
+def test_flow_with_other_parameters(bridge, port, kw):
+    """Same parameters as the reference, whatever they are (rvdd_tvl1_params): zoom factors other than 0.5 take the
+    generic Gaussian + bicubic resampling path and other tap radii, fscale > 0 skips the finest level."""
+    from rvdd_release_b200.bridge import TVL1Params
+    I0, I1 = synth.gray_pair(72, 110, "iso3200")
+    want = port.multiscale(I0, I1, **kw)
+    p = TVL1Params()
+    bridge.lib.rvdd_default_params(p)
+    for k, v in kw.items():
+        setattr(p, "lambda_" if k == "lam" else k, v)
+    gray = torch.from_numpy(np.stack([I0, I1])).cuda()
+    flow = bridge.tvl1_flow(gray, [1], [0], params=p, check=True)[0].cpu().numpy()
+    assert epe(flow, want) <= EPE_TOL
+    assert np.array_equal(flow, want)

@@ -131,3 +131,18 @@ def test_demosaic_ref_matches_reference_golden(path):
     y = demosaic_ref.hamilton_adam(g["x"], str(g["pattern"]))
     assert y.shape == g["y"].shape and np.abs(y - g["y"]).max() <= 1e-6
     assert np.array_equal(demosaic_ref.remosaick(g["y"][:, :3], "gbrg"), g["remosaick"])
+
+
+PARAM_SETS = [dict(zfactor=0.7, nwarps=3, tau=0.2, lam=0.1, theta=0.25, epsilon=0.02),
+              dict(zfactor=0.5, nwarps=2, nscales=3, lam=0.3, theta=0.4, epsilon=0.005),
+              dict(zfactor=0.35, nwarps=4, fscale=1),
+              dict(zfactor=0.8, nscales=4, nwarps=1)]
+
+
+@pytest.mark.parametrize("kw", PARAM_SETS)
+def test_port_matches_compiled_reference_with_other_parameters(port, reflib, kw):
+    """tau, lambda, theta, nscales, fscale, zfactor, nwarps, epsilon away from the bridge's defaults (the north star's
+    "same parameters" clause): the port still equals the reference's Dual_TVL1_optic_flow_multiscale bit for bit,
+    including the generic zoom_out path (zoom factors other than 0.5: fractional bicubic resampling)."""
+    I0, I1 = synth.gray_pair(72, 110, "iso3200")
+    assert np.array_equal(port.multiscale(I0, I1, **kw), reflib.multiscale(I0, I1, **kw))

@@ -528,10 +528,25 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
                 const float *c1 = UB(uc, 0), *c2 = UB(uc, 1);
                 float *f1 = UB(uc ^ 1, 0), *f2 = UB(uc ^ 1, 1);
                 const float zx = A.zfx[s - 1], zy = A.zfy[s - 1];
-                for (int i = gtid; i < fn; i += gthreads) {
-                    const int y = i / fx_n, x = i - y * fx_n;
-                    f1[i] = zoom_in_px(c1, x, y, nx, ny, zx, zy, A.zoom_mul);
-                    f2[i] = zoom_in_px(c2, x, y, nx, ny, zx, zy, A.zoom_mul);
+                if (fx_n == 2 * nx && fy_n == 2 * ny) {
+                    // exact factor 2: one thread per coarse pixel writes its 2x2 fine block (shared taps, zero fractions)
+                    for (int i = gtid; i < n; i += gthreads) {
+                        const int Y = i / nx, X = i - Y * nx;
+                        float b1[2][2], b2[2][2];
+                        zoom_in_2x_block(c1, X, Y, nx, ny, A.zoom_mul, b1);
+                        zoom_in_2x_block(c2, X, Y, nx, ny, A.zoom_mul, b2);
+                        const long long o = (long long)(2 * Y) * fx_n + 2 * X;
+                        *reinterpret_cast<float2 *>(f1 + o) = make_float2(b1[0][0], b1[0][1]);
+                        *reinterpret_cast<float2 *>(f1 + o + fx_n) = make_float2(b1[1][0], b1[1][1]);
+                        *reinterpret_cast<float2 *>(f2 + o) = make_float2(b2[0][0], b2[0][1]);
+                        *reinterpret_cast<float2 *>(f2 + o + fx_n) = make_float2(b2[1][0], b2[1][1]);
+                    }
+                } else {
+                    for (int i = gtid; i < fn; i += gthreads) {
+                        const int y = i / fx_n, x = i - y * fx_n;
+                        f1[i] = zoom_in_px(c1, x, y, nx, ny, zx, zy, A.zoom_mul);
+                        f2[i] = zoom_in_px(c2, x, y, nx, ny, zx, zy, A.zoom_mul);
+                    }
                 }
                 uc ^= 1;
             } else {

@@ -438,6 +438,30 @@ RVDD_HD float zoom_in_px(const float *coarse, int x, int y, int nx, int ny, floa
     return FMUL(rvdd_bicubic_clamped(coarse, FDIV((float)x, zx), FDIV((float)y, zy), nx, ny), mul);
 }
 
+// The same upsampling when the fine level is EXACTLY twice the coarse one in both directions (every level of an even-sized
+// pyramid, e.g. 1280x720 -> 640x360 -> 320x180): the sample positions x / 2.0f are integers or integers + 0.5, and the
+// four fine pixels (2X + i, 2Y + j) of coarse pixel (X, Y) share their 16 taps.  With a zero fraction the Keys cubic
+// returns its second sample (v1 + 0.5 * 0 * (...) = v1), so per block only six of the twenty cubics are evaluated
+// (108 double operations instead of 360) and the taps are loaded and converted once.  Identical values (up to the sign
+// of a zero).  out[j][i] = fine pixel (2X + i, 2Y + j).
+RVDD_HD void zoom_in_2x_block(const float *coarse, int X, int Y, int nx, int ny, float mul, float (&out)[2][2])
+{
+    const int xi[4] = {rvdd_clampi(X - 1, nx), X, rvdd_clampi(X + 1, nx), rvdd_clampi(X + 2, nx)};
+    const int yi[4] = {rvdd_clampi(Y - 1, ny), Y, rvdd_clampi(Y + 1, ny), rvdd_clampi(Y + 2, ny)};
+    double d[4][4];                                        // d[column][row]
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int r = 0; r < 4; r++) d[c][r] = (double)coarse[xi[c] + (long long)nx * yi[r]];
+    double colh[4];                                        // columns interpolated at ty = 0.5
+#pragma unroll
+    for (int c = 0; c < 4; c++) colh[c] = rvdd_keys_half(d[c][0], d[c][1], d[c][2], d[c][3], 0.5);
+    out[0][0] = FMUL((float)d[1][1], mul);
+    out[0][1] = FMUL((float)rvdd_keys_half(d[0][1], d[1][1], d[2][1], d[3][1], 0.5), mul);
+    out[1][0] = FMUL((float)colh[1], mul);
+    out[1][1] = FMUL((float)rvdd_keys_half(colh[0], colh[1], colh[2], colh[3], 0.5), mul);
+}
+
 // strip decomposition of an nx*ny image over `nwarps` warps with V pixels per lane: column segments of 32*V
 // pixels, `rows` rows per strip.
 struct StripPlan {

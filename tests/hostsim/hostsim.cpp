@@ -162,6 +162,15 @@ extern "C" int hs_tvl1flow(const float *I0, const float *I1, float *u, int nx0, 
         if (s > 0) {
             const int fw = nx[s - 1], fh = ny[s - 1];
             const float zx = ((float)fw / w_), zy = ((float)fh / h_);
+            if (fw == 2 * w_ && fh == 2 * h_) {           // the device's exact-factor-2 path: 2x2 blocks with shared taps
+                for (int i = 0; i < n; i++)
+                    for (int comp = 0; comp < 2; comp++) {
+                        float blk[2][2];
+                        zoom_in_2x_block(ub[uc][comp], i % w_, i / w_, w_, h_, zoom_mul, blk);
+                        for (int j = 0; j < 2; j++)
+                            for (int k = 0; k < 2; k++) ub[uc ^ 1][comp][(size_t)(2 * (i / w_) + j) * fw + 2 * (i % w_) + k] = blk[j][k];
+                    }
+            } else
             for (int i = 0; i < fw * fh; i++) {
                 ub[uc ^ 1][0][i] = zoom_in_px(ub[uc][0], i % fw, i / fw, w_, h_, zx, zy, zoom_mul);
                 ub[uc ^ 1][1][i] = zoom_in_px(ub[uc][1], i % fw, i / fw, w_, h_, zx, zy, zoom_mul);

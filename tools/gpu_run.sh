@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q -x 2>&1 | grep -v Warning | tail -25
-python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/j_base.json 2> gpurun_out/j_base.err
-ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:solver_kernel|warp_|gauss_|resample_|gray_|minmax_|setup_|interleave_|demosaic_|upsample2_|remosaick" -c 300 --csv --log-file gpurun_out/launches_r1j.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
+python -m pytest tests/test_gpu_parity.py -m gpu -q -x 2>&1 | grep -v Warning | tail -3
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/k_base.json 2> gpurun_out/k_base.err
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/k_base2.json 2> gpurun_out/k_base2.err

@@ -335,27 +335,9 @@ __device__ __forceinline__ double iterate_group(const SolverArgs &A, int group, 
 // rows; a warp marches down its tile WC_BATCH rows at a time, so three of the four tap rows of every bicubic window
 // were touched by the same warp one trip earlier and come out of L1, and the flow / I0 values of the next trip are
 // requested before the double-precision arithmetic of the current one starts.
-// The taps are not gathered from global memory: per trip the warp stages the bounding box of all its taps --
-// (32 + 3 + flow spread) x (WC_BATCH + 3 + spread) source pixels of I1, I1x, I1y -- in its slice of the (idle) row-staging
-// ring with cp.async, ONE TRIP AHEAD: the box of trip t+1 is in flight while trip t does its 270 double-precision
-// operations per pixel, so the dependent gather latency (half of the phase's stall samples before) is off the critical
-// path, and the gathers themselves become coalesced row copies plus shared-memory reads.  A trip whose box does not fit
-// (rough flow) gathers from global memory as before.
-#define WC_BOX ((ST_STAGES * ST_ROW) / 6)      // floats per image and buffer (two buffers x three images in the ring slice)
-
-__device__ __forceinline__ void cp_async_f32(float *dst_smem, const float *src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
-}
-
-struct WcBox {
-    int lox, loy, bw, bh;
-    bool staged;
-};
-
 __device__ __forceinline__ void warp_consts_group(const float *I0, const float *I1, const float *I1x, const float *I1y,
                                                   const float *u1, const float *u2, float *gx, float *gy, float *rc, int nx,
-                                                  int ny, int gwarp, int gwarps, float *ring)
+                                                  int ny, int gwarp, int gwarps)
 {
     const int lane = threadIdx.x & 31;
     const int ncolt = (nx + 31) >> 5;
@@ -373,90 +355,31 @@ __device__ __forceinline__ void warp_consts_group(const float *I0, const float *
         const int tyi = t / ncolt, cx = t - tyi * ncolt;
         const int x = cx * 32 + lane, y0 = tyi * TR, y1 = min(ny, y0 + TR);
         const bool lane_on = x < nx;
-        float na[WC_BATCH], nb[WC_BATCH], ni0[WC_BATCH];
+        float a[WC_BATCH], b[WC_BATCH], i0[WC_BATCH], na[WC_BATCH], nb[WC_BATCH], ni0[WC_BATCH];
         int px[WC_BATCH], py[WC_BATCH];
         bool act[WC_BATCH];
-        auto request = [&](int y) {                      // flow + I0 of the trip starting at row y
+#pragma unroll
+        for (int k = 0; k < WC_BATCH; k++) {
+            px[k] = x;
+            const bool on = lane_on && y0 + k < y1;
+            const long long i = on ? (long long)(y0 + k) * nx + x : 0;
+            na[k] = u1[i]; nb[k] = u2[i]; ni0[k] = I0[i];
+        }
+        for (int y = y0; y < y1; y += WC_BATCH) {
 #pragma unroll
             for (int k = 0; k < WC_BATCH; k++) {
-                const bool on = lane_on && y + k < y1;
-                const long long i = on ? (long long)(y + k) * nx + x : 0;
+                a[k] = na[k]; b[k] = nb[k]; i0[k] = ni0[k];
+                py[k] = y + k;
+                act[k] = lane_on && y + k < y1;
+            }
+#pragma unroll
+            for (int k = 0; k < WC_BATCH; k++) {          // next trip's inputs: in flight during this trip's arithmetic
+                const bool on = lane_on && y + WC_BATCH + k < y1;
+                const long long i = on ? (long long)(y + WC_BATCH + k) * nx + x : 0;
                 na[k] = u1[i]; nb[k] = u2[i]; ni0[k] = I0[i];
             }
-        };
-        auto prep = [&](WcTrip<WC_BATCH> &T, int y) {    // consumes the requested values
-#pragma unroll
-            for (int k = 0; k < WC_BATCH; k++) { px[k] = x; py[k] = y + k; act[k] = lane_on && y + k < y1; }
-            wc_prep<WC_BATCH>(T, na, nb, ni0, px, py, act, nx, ny);
-        };
-        // bounding box of the taps of the samples that stay inside the image, and the asynchronous copy of that box
-        auto stage = [&](const WcTrip<WC_BATCH> &T, int buf) {
-            WcBox B;
-            int lox = 0x7fffffff, hix = -1, loy = 0x7fffffff, hiy = -1;
-#pragma unroll
-            for (int k = 0; k < WC_BATCH; k++)
-                if (T.in[k]) {
-                    lox = min(lox, T.bx0[k]); hix = max(hix, T.bx0[k] + 3);
-                    loy = min(loy, T.by0[k]); hiy = max(hiy, T.by0[k] + 3);
-                }
-            B.lox = __reduce_min_sync(0xffffffffu, lox); hix = __reduce_max_sync(0xffffffffu, hix);
-            B.loy = __reduce_min_sync(0xffffffffu, loy); hiy = __reduce_max_sync(0xffffffffu, hiy);
-            B.bw = hix - B.lox + 1; B.bh = hiy - B.loy + 1;
-            B.staged = hix >= 0 && B.bw * B.bh <= WC_BOX;             // warp-uniform
-            if (B.staged) {
-                float *dst = ring + buf * 3 * WC_BOX;
-                for (int r = 0; r < B.bh; r++) {
-                    const long long go = (long long)(B.loy + r) * nx + B.lox;
-                    for (int c = lane; c < B.bw; c += 32) {
-                        cp_async_f32(dst + r * B.bw + c, I1 + go + c);
-                        cp_async_f32(dst + WC_BOX + r * B.bw + c, I1x + go + c);
-                        cp_async_f32(dst + 2 * WC_BOX + r * B.bw + c, I1y + go + c);
-                    }
-                }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");      // one group per trip, empty or not
-            return B;
-        };
-
-        WcTrip<WC_BATCH> cur, nxt;
-        request(y0);
-        prep(cur, y0);
-        request(y0 + WC_BATCH);
-        __syncwarp();                                                 // the previous tile's reads of the ring are done
-        WcBox bc = stage(cur, 0), bn;
-        int buf = 0;
-#pragma unroll 1
-        for (int y = y0; y < y1; y += WC_BATCH, buf ^= 1) {
-            prep(nxt, y + WC_BATCH);                                  // rows past y1 are inactive: nothing to stage
-            request(y + 2 * WC_BATCH);
-            bn = stage(nxt, buf ^ 1);                                 // in flight during this trip's arithmetic
-            float w0[WC_BATCH], wx[WC_BATCH], wy[WC_BATCH];
-            if (bc.staged) {
-                asm volatile("cp.async.wait_group 1;" ::: "memory");  // this trip's box (all but the newest group) landed
-                __syncwarp();
-                const float *box = ring + buf * 3 * WC_BOX;
-#pragma unroll
-                for (int img = 0; img < 3; img++) {
-                    float v[WC_BATCH][4][4];
-#pragma unroll
-                    for (int k = 0; k < WC_BATCH; k++) wc_taps<WC_BATCH>(box + img * WC_BOX, bc.bw, bc.lox, bc.loy, cur, k, v[k]);
-#pragma unroll
-                    for (int k = 0; k < WC_BATCH; k++) {
-                        const float w = cur.in[k] ? rvdd_bicubic_cell(v[k], cur.tx[k], cur.ty[k]) : 0.f;
-                        if (img == 0) w0[k] = w;
-                        else if (img == 1) wx[k] = w;
-                        else wy[k] = w;
-                    }
-                }
-            } else {
-                wc_direct<WC_BATCH>(I1, I1x, I1y, cur, nx, w0, wx, wy);
-            }
-            wc_store<WC_BATCH>(cur, w0, wx, wy, nx, gx, gy, rc);
-            __syncwarp();                                             // everybody is done with this buffer: the trip after next reuses it
-            cur = nxt;
-            bc = bn;
+            warp_consts_eval<WC_BATCH>(I1, I1x, I1y, a, b, i0, px, py, act, nx, ny, gx, gy, rc);
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
 }
 
@@ -551,7 +474,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
                     const unsigned long long tp0 = stamping ? now_ns() : 0ULL;
                     // ---- warp constants (:143-159): bicubic samples of I1, I1x, I1y at x + u
                     const float *u1 = UB(uc, 0), *u2 = UB(uc, 1);
-                    warp_consts_group(I0, I1, I1x, I1y, u1, u2, gx, gy, rc, nx, ny, gwarp, gwarps, reinterpret_cast<float *>(T.base));
+                    warp_consts_group(I0, I1, I1x, I1y, u1, u2, gx, gy, rc, nx, ny, gwarp, gwarps);
                     if (!group_sync(g, &s_flag)) return;
                     const unsigned long long tp1 = stamping ? now_ns() : 0ULL;
 

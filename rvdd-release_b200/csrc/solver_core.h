@@ -354,90 +354,53 @@ RVDD_HD void cgrad_px(const float *I1, int x, int y, int nx, int ny, float *dx, 
 // reads element 0 sixteen times through zero strides and is zeroed by a select -- so that the compiler can issue the
 // flow loads of all U pixels, then the 16 * U taps of each image, before the double-precision arithmetic starts.
 // idx[k] < 0 marks an unused slot.
-// Everything one trip (U pixels) of the warp-constants phase needs besides the image taps.
-template <int U> struct WcTrip {
-    float a[U], b[U], i0[U];        // flow and I0 at the pixels
-    float tx[U], ty[U];             // bicubic fractions
-    int bx0[U], by0[U];             // coordinates of tap (0, 0); (0, 0) with zero strides when the sample leaves the image
-    int px[U], py[U];
-    bool in[U], act[U];
-};
-
-template <int U>
-RVDD_HD void wc_prep(WcTrip<U> &T, const float (&a)[U], const float (&b)[U], const float (&i0)[U], const int (&px)[U],
-                     const int (&py)[U], const bool (&act)[U], int nx, int ny)
-{
-#pragma unroll
-    for (int k = 0; k < U; k++) {
-        T.a[k] = a[k]; T.b[k] = b[k]; T.i0[k] = i0[k]; T.px[k] = px[k]; T.py[k] = py[k]; T.act[k] = act[k];
-        const float uu = FADD((float)px[k], a[k]), vv = FADD((float)py[k], b[k]);
-        T.in[k] = act[k] && rvdd_inside_strict(uu, vv, nx, ny);
-        const int bx = T.in[k] ? (int)uu : 1, by = T.in[k] ? (int)vv : 1;
-        T.tx[k] = FSUB(uu, (float)bx);
-        T.ty[k] = FSUB(vv, (float)by);
-        T.bx0[k] = bx - 1;
-        T.by0[k] = by - 1;
-    }
-}
-
-// the 16 taps of pixel k of the trip out of an image (or a staged box) with row pitch `pitch` whose element (0, 0) is
-// image pixel (ox, oy); a sample that leaves the image reads element 0 sixteen times.  v[column][row]
-template <int U>
-RVDD_HD void wc_taps(const float *src, int pitch, int ox, int oy, const WcTrip<U> &T, int k, float (&v)[4][4])
-{
-    const int rs = T.in[k] ? pitch : 0, cs = T.in[k] ? 1 : 0;
-    const float *q = src + (T.in[k] ? (long long)(T.by0[k] - oy) * pitch + (T.bx0[k] - ox) : 0);
-#pragma unroll
-    for (int r = 0; r < 4; r++)
-#pragma unroll
-        for (int c = 0; c < 4; c++) v[c][r] = q[r * rs + c * cs];
-}
-
-template <int U>
-RVDD_HD void wc_store(const WcTrip<U> &T, const float (&w0)[U], const float (&wx)[U], const float (&wy)[U], int nx, float *gx,
-                      float *gy, float *rc)
-{
-#pragma unroll
-    for (int k = 0; k < U; k++) {
-        if (!T.act[k]) continue;
-        const long long i = (long long)T.py[k] * nx + T.px[k];
-        gx[i] = wx[k];
-        gy[i] = wy[k];
-        rc[i] = FSUB(FSUB(FSUB(w0[k], FMUL(wx[k], T.a[k])), FMUL(wy[k], T.b[k])), T.i0[k]);
-    }
-}
-
-// One trip with the taps gathered straight from the three images.
-template <int U>
-RVDD_HD void wc_direct(const float *I1, const float *I1x, const float *I1y, const WcTrip<U> &T, int nx, float (&w0)[U],
-                       float (&wx)[U], float (&wy)[U])
-{
-    float v[U][4][4];
-#pragma unroll
-    for (int img = 0; img < 3; img++) {
-        const float *src = img == 0 ? I1 : (img == 1 ? I1x : I1y);
-#pragma unroll
-        for (int k = 0; k < U; k++) wc_taps<U>(src, nx, 0, 0, T, k, v[k]);
-#pragma unroll
-        for (int k = 0; k < U; k++) {
-            const float w = T.in[k] ? rvdd_bicubic_cell(v[k], T.tx[k], T.ty[k]) : 0.f;
-            if (img == 0) w0[k] = w;
-            else if (img == 1) wx[k] = w;
-            else wy[k] = w;
-        }
-    }
-}
-
 template <int U>
 RVDD_HD void warp_consts_eval(const float *I1, const float *I1x, const float *I1y, const float (&a)[U], const float (&b)[U],
                               const float (&i0)[U], const int (&px)[U], const int (&py)[U], const bool (&act)[U], int nx,
                               int ny, float *gx, float *gy, float *rc)
 {
-    WcTrip<U> T;
-    wc_prep<U>(T, a, b, i0, px, py, act, nx, ny);
+    float tx[U], ty[U];
+    long long o[U];
+    int rs[U], cs[U];
+    bool in[U];
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+        const float uu = FADD((float)px[k], a[k]), vv = FADD((float)py[k], b[k]);
+        in[k] = act[k] && rvdd_inside_strict(uu, vv, nx, ny);
+        const int bx = in[k] ? (int)uu : 1, by = in[k] ? (int)vv : 1;
+        tx[k] = FSUB(uu, (float)bx);
+        ty[k] = FSUB(vv, (float)by);
+        rs[k] = in[k] ? nx : 0;
+        cs[k] = in[k] ? 1 : 0;
+        o[k] = in[k] ? (long long)(by - 1) * nx + (bx - 1) : 0;
+    }
     float w0[U], wx[U], wy[U];
-    wc_direct<U>(I1, I1x, I1y, T, nx, w0, wx, wy);
-    wc_store<U>(T, w0, wx, wy, nx, gx, gy, rc);
+#pragma unroll
+    for (int img = 0; img < 3; img++) {
+        const float *src = img == 0 ? I1 : (img == 1 ? I1x : I1y);
+        float v[U][4][4];
+#pragma unroll
+        for (int k = 0; k < U; k++)
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) v[k][c][r] = src[o[k] + r * rs[k] + c * cs[k]];
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            const float w = in[k] ? rvdd_bicubic_cell(v[k], tx[k], ty[k]) : 0.f;
+            if (img == 0) w0[k] = w;
+            else if (img == 1) wx[k] = w;
+            else wy[k] = w;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+        if (!act[k]) continue;
+        const long long i = (long long)py[k] * nx + px[k];
+        gx[i] = wx[k];
+        gy[i] = wy[k];
+        rc[i] = FSUB(FSUB(FSUB(w0[k], FMUL(wx[k], a[k])), FMUL(wy[k], b[k])), i0[k]);
+    }
 }
 
 // The same for U linear pixel indices (idx[k] < 0 marks an unused slot), loads included.

@@ -267,7 +267,7 @@ def run_ours(args, rank, local_rank, world):
         br.wait_host(1)
 
     e2e_run(2)
-    e2e_steps = max(10, args.steps)          # a streaming pipeline: enough steps that fill + drain (one upload, one download) amortise
+    e2e_steps = max(20, args.steps)          # a streaming pipeline: enough steps that fill + drain (one upload, one download) amortise
     barrier()
     t0 = time.perf_counter()
     e2e_run(e2e_steps)

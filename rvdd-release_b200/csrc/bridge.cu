@@ -626,17 +626,21 @@ extern "C" int rvdd_flow_and_warp_host_submit(rvdd_ctx *c, int slot, const float
         CK(cudaGetLastError());
     }
     if (warped_host) {
-        // single_warp(img1 = source frame, flow) in the frames' own HWC layout (flow_utils.py:105-122, :154)
-        for (int k = 0; k < npairs; k++) {
+        // single_warp(img1 = source frame, flow) in the frames' own HWC layout (flow_utils.py:105-122, :154); runs of
+        // consecutive source frames (a video: sources t-1 = 0, 1, 2, ...) go out as one batched launch
+        for (int k = 0; k < npairs;) {
+            int run = 1;
+            while (k + run < npairs && src[k + run] == src[k] + run && run < 65535) run++;
             WarpArgs a;
             a.x = d_frames + (long long)src[k] * n * ch;
             a.flow = d_flow + (long long)k * 2 * n;
             a.out = d_warp + (long long)k * n * ch;
             a.mask = nullptr;
-            a.B = 1; a.C = ch; a.H = h; a.W = w;
+            a.B = run; a.C = ch; a.H = h; a.W = w;
             a.xs_b = a.os_b = n * ch; a.xs_c = a.os_c = 1; a.xs_h = a.os_h = (long long)w * ch; a.xs_w = a.os_w = ch;
             a.fh = h; a.fw = w; a.flow_mul = 1.0f; a.interp = 1;
             CK(launch_warp(a, st));
+            k += run;
         }
     }
     CK(cudaMemcpyAsync(c->slot_status_host[slot], c->status_dev, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -126,8 +126,9 @@ gauss_tile_kernel(const float *const *__restrict__ srcs, const float *__restrict
     constexpr int GB = 4;                    // outputs per thread and pass
     constexpr int in_w = STEP * GT_X + 2 * R, in_h = STEP * TY + 2 * R;
     constexpr int in_p = in_w | 1;           // odd pitch: lanes walking down a column of doubles hit distinct banks
+    constexpr int row_p = GT_X + 1;          // odd pitch again: the row pass writes s_row with lanes walking down a column
     double *s_in = smem_d;                   // [in_h][in_p]
-    double *s_row = smem_d + in_h * in_p;    // [in_h][GT_X]   (row-pass results at the columns the outputs need)
+    double *s_row = smem_d + in_h * in_p;    // [in_h][row_p]  (row-pass results at the columns the outputs need)
     const int ox = blockIdx.x * GT_X * STEP, oy = blockIdx.y * TY * STEP;        // tile origin in the input
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
 
@@ -137,13 +138,29 @@ gauss_tile_kernel(const float *const *__restrict__ srcs, const float *__restrict
         lo = ord2f(slots[2 * k]);
         den = FSUB(ord2f(slots[2 * k + 1]), lo);
     }
-    for (int r = wrp; r < in_h; r += 8) {
-        const int gy = rvdd_reflect(oy - R + r, ny);
-        const float *srow = src + (long long)gy * nx;
-        for (int c = lane; c < in_w; c += 32) {
-            float v = __ldg(srow + rvdd_reflect(ox - R + c, nx));
-            if (NORM && den > 0.f) v = rvdd_normalize_px(v, lo, den);
-            s_in[r * in_p + c] = (double)v;
+    // staging: all loads of a thread are issued before the first conversion (fully unrolled, loads into registers first)
+    {
+        constexpr int NR = (in_h + 7) / 8, NC = (in_w + 31) / 32;
+        float v[NR][NC];
+#pragma unroll
+        for (int a = 0; a < NR; a++) {
+            const int r = wrp + 8 * a;
+            const float *srow = src + (long long)rvdd_reflect(oy - R + min(r, in_h - 1), ny) * nx;
+#pragma unroll
+            for (int b = 0; b < NC; b++) v[a][b] = __ldg(srow + rvdd_reflect(ox - R + min(lane + 32 * b, in_w - 1), nx));
+        }
+#pragma unroll
+        for (int a = 0; a < NR; a++) {
+            const int r = wrp + 8 * a;
+#pragma unroll
+            for (int b = 0; b < NC; b++) {
+                const int c = lane + 32 * b;
+                if (r < in_h && c < in_w) {
+                    float t = v[a][b];
+                    if (NORM && den > 0.f) t = rvdd_normalize_px(t, lo, den);
+                    s_in[r * in_p + c] = (double)t;
+                }
+            }
         }
     }
     __syncthreads();
@@ -161,7 +178,7 @@ gauss_tile_kernel(const float *const *__restrict__ srcs, const float *__restrict
             double acc = DMUL(taps.B[0], w[STEP * o + RR]);
 #pragma unroll
             for (int j = 1; j <= RR; j++) acc = DADD(acc, DMUL(taps.B[j], DADD(w[STEP * o + RR - j], w[STEP * o + RR + j])));
-            s_row[r * GT_X + c0 + o] = (double)(float)acc;
+            s_row[r * row_p + c0 + o] = (double)(float)acc;
         }
     }
     __syncthreads();
@@ -170,10 +187,10 @@ gauss_tile_kernel(const float *const *__restrict__ srcs, const float *__restrict
     const int qx = blockIdx.x * GT_X, qy = blockIdx.y * TY;                      // tile origin in the output
     for (int i = threadIdx.x; i < (TY / GB) * GT_X; i += 256) {
         const int c = i % GT_X, r0 = (i / GT_X) * GB;
-        const double *col = s_row + (STEP * r0) * GT_X + c;
+        const double *col = s_row + (STEP * r0) * row_p + c;
         double w[2 * RR + STEP * (GB - 1) + 1];
 #pragma unroll
-        for (int k = 0; k < 2 * RR + STEP * (GB - 1) + 1; k++) w[k] = col[k * GT_X];
+        for (int k = 0; k < 2 * RR + STEP * (GB - 1) + 1; k++) w[k] = col[k * row_p];
 #pragma unroll
         for (int o = 0; o < GB; o++) {
             double acc = DMUL(taps.B[0], w[STEP * o + RR]);
@@ -187,7 +204,7 @@ gauss_tile_kernel(const float *const *__restrict__ srcs, const float *__restrict
 static size_t gauss_smem(int R, int step)
 {
     const int ty = step == 2 ? GT_Y / 2 : GT_Y;
-    return sizeof(double) * ((size_t)(step * ty + 2 * R) * ((step * GT_X + 2 * R) | 1) + (size_t)(step * ty + 2 * R) * GT_X);
+    return sizeof(double) * ((size_t)(step * ty + 2 * R) * ((step * GT_X + 2 * R) | 1) + (size_t)(step * ty + 2 * R) * (GT_X + 1));
 }
 
 template <bool NORM, bool DEC, int RR, typename... Args>

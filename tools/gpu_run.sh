@@ -1,4 +1,7 @@
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_parity.py -m gpu -q -x 2>&1 | grep -v Warning | tail -3
-python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/p_base.json 2> gpurun_out/p_base.err
-ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:solver_kernel|warp_|gauss_|resample_|gray_|minmax_|setup_|interleave_|demosaic_|upsample2_|remosaick" -c 300 --csv --log-file gpurun_out/launches_r1p.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
+python -m pytest tests -m gpu -q 2>&1 | grep -v Warning | tail -3
+python bench.py > gpurun_out/q_default.json 2> gpurun_out/q_default.err
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/q_ref.json 2> gpurun_out/q_ref.err
+ncu --set full --clock-control none --import-source on -k regex:solver_kernel -s 3 -c 1 -o gpurun_out/prof_solver_r1q -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_solver.log 2>&1
+python profiles/bench_warp.py > gpurun_out/stage_kernels.jsonl 2>gpurun_out/stage_kernels.err
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log

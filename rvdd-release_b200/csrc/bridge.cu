@@ -549,6 +549,7 @@ static int parse_pattern(const char *pattern, int *ry, int *rx, int *by, int *bx
 
 extern "C" int rvdd_demosaic_ha_dev(const float *x, float *y, int B, int H, int W, const char *pattern, void *stream)
 {
+    if (B == 0) return 0;
     if (!x || !y) return fail("rvdd_demosaic_ha_dev: null argument");
     if (B < 0 || H < 1 || W < 1 || B > 65535) return fail("rvdd_demosaic_ha_dev: bad geometry");
     int ry = 0, rx = 0, by = 0, bx = 0;
@@ -561,6 +562,7 @@ extern "C" int rvdd_demosaic_ha_dev(const float *x, float *y, int B, int H, int 
 extern "C" int rvdd_remosaick_gray_dev(const float *rgb, float *gray, int B, int H, int W, const char *pattern, float add,
                                        float mul, void *stream)
 {
+    if (B == 0) return 0;
     if (!rgb || !gray) return fail("rvdd_remosaick_gray_dev: null argument");
     if (B < 0 || H < 1 || W < 1 || B > 65535 || H > 65535) return fail("rvdd_remosaick_gray_dev: bad geometry");
     int ry = 0, rx = 0, by = 0, bx = 0;

@@ -70,3 +70,12 @@ def test_product_never_imports_oracle():
                     if needle == "hostsim" and f.endswith(".h"):
                         continue            # the headers only mention the host-compiled unit tests in a comment
                     assert needle not in src, (os.path.join(dirpath, f), needle)
+
+
+def test_hostbind_is_best_effort():
+    """NUMA pinning helper: parses cpulists, and never fails where there is no GPU / no sysfs entry."""
+    from rvdd_release_b200 import hostbind
+    assert hostbind._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert hostbind._parse_cpulist("") == set()
+    info = hostbind.bind_to_gpu(0)
+    assert info["gpu"] == 0 and isinstance(info["bound"], bool)

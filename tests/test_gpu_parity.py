@@ -401,3 +401,21 @@ def test_flow_with_other_parameters(bridge, port, kw):
     flow = bridge.tvl1_flow(gray, [1], [0], params=p, check=True)[0].cpu().numpy()
     assert epe(flow, want) <= EPE_TOL
     assert np.array_equal(flow, want)
+
+
+def test_demosaic_argument_errors(bridge):
+    """Error behaviour of the new entry points: status code + message, never a crash or a silent fallback."""
+    from rvdd_release_b200.bridge import BridgeError
+    from rvdd_release_b200.hamilton_adam import HamiltonAdam
+    x = torch.zeros(1, 4, 8, 8, device="cuda")
+    with pytest.raises(BridgeError):
+        bridge.demosaic(x, "rgbg")                    # red and blue must sit on a diagonal
+    with pytest.raises(BridgeError):
+        bridge.demosaic(torch.zeros(1, 6, 8, 8, device="cuda"), "gbrg")
+    with pytest.raises(BridgeError):
+        bridge.demosaic(x.cpu(), "gbrg")              # no CPU fallback
+    with pytest.raises(ValueError):
+        HamiltonAdam("xyzw")
+    with pytest.raises(BridgeError):
+        bridge.remosaick_gray(torch.zeros(1, 3, 7, 8, device="cuda"))
+    assert bridge.demosaic(torch.zeros(0, 4, 8, 8, device="cuda")).shape == (0, 3, 16, 16)

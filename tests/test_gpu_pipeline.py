@@ -98,26 +98,28 @@ def test_recurrent_convunet_feat_future_psnr_within_0p02_db(bridge):
     from oracle import warp_ref
 
     def run(ours):
-        """ours=True: csrc warps writing into the network's buffers; False: the reference's grid_sample warp on the GPU
-        (oracle/warp_ref.py on CUDA tensors) -- same cuDNN denoiser, so the difference isolates the alignment path."""
+        """ours=True: rvdd_release_b200.recurrent_align.FrameAligner (csrc warps writing into the network's buffers);
+        False: the reference's grid_sample warp on the GPU (oracle/warp_ref.py on CUDA tensors) -- same cuDNN denoiser,
+        so the difference isolates the alignment path."""
+        from rvdd_release_b200.recurrent_align import FrameAligner
+        al = FrameAligner(depth=1, future_depth=1, feature_channels=48)
+        al.reset(n[0:1])
         lastden = n[0:1]
         lastfeat = torch.zeros(1, 48, 2 * h, 2 * w, device="cuda")
         netinput = torch.empty(1, 9, 2 * h, 2 * w, device="cuda")
-        featinput = torch.empty_like(lastfeat)
         psnrs, den = [], None
         for t in range(1, T + 1):
             if ours:
-                bridge.warp(lastden, flows[t - 1:t], "bicubic", flow_mul=2.0, want_mask=False, out=netinput[:, 0:3])
-                bridge.warp(n[t + 1:t + 2], flows[T + t - 1:T + t], "bicubic", flow_mul=2.0, want_mask=False, out=netinput[:, 6:9])
-                bridge.warp(lastfeat, flows[t - 1:t], "bicubic", flow_mul=2.0, want_mask=False, out=featinput)
+                netinput, featinput = al.step(n[t:t + 1], flows[t - 1:t], [n[t + 1:t + 2]], [flows[T + t - 1:T + t]])
             else:
                 up, fup = warp_ref.upsample_factor_2(flows[t - 1:t], 2), warp_ref.upsample_factor_2(flows[T + t - 1:T + t], 2)
                 netinput[:, 0:3] = warp_ref.warp(lastden, up, "bicubic")[0]
+                netinput[:, 3:6] = n[t]
                 netinput[:, 6:9] = warp_ref.warp(n[t + 1:t + 2], fup, "bicubic")[0]
                 featinput = warp_ref.warp(lastfeat, up, "bicubic")[0]
-            netinput[:, 3:6] = n[t]
             den, feat = net(netinput, featinput)
             lastden, lastfeat = den.clone(), feat.clone()
+            al.update(lastden, lastfeat)
             psnrs.append(_psnr(den, gt[t:t + 1]))
         return np.array(psnrs), den[0].cpu()
 

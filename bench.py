@@ -311,7 +311,7 @@ def run_ours(args, rank, local_rank, world):
         cpu = {"value": 2 / dt, "unit": "pairs/s", "cores": threads, "kind": kind,
                "sample": "2 pairs (frames 0-2) of the benchmarked sequence: reference C tvl1flow (OpenMP) + torch-CPU warp"}
 
-    launches_per_step = 1 + (3 + 2 * (S - 1) + 1) + 1     # gray | setup, minmax, presmooth, (gauss, resample)/level, solver | warp
+    launches_per_step = 1 + (3 + (S - 1) + 1) + 1         # gray | setup, minmax, presmooth, fused zoom_out per level, solver | warp
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -13,11 +13,24 @@ import torch.nn.functional as F
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import warp_ref  # noqa: E402  (the torch restatement of util/flow_utils.py, as the comparison arm only)
 from rvdd_release_b200 import flow_utils, synth  # noqa: E402
 from rvdd_release_b200.recurrent_align import FrameAligner  # noqa: E402
 
 H, W = 720, 1280
+
+
+def torch_warp(x, flow):
+    """The reference's formulation (util/flow_utils.py:70-102) in torch on the GPU: the comparison arm."""
+    B, C, Hh, Ww = x.shape
+    ys, xs = torch.meshgrid(torch.arange(Hh, device=x.device), torch.arange(Ww, device=x.device), indexing="ij")
+    grid = torch.stack((xs, ys), 0)[None].float() + flow
+    gx = 2.0 * grid[:, 0] / (Ww - 1) - 1.0
+    gy = 2.0 * grid[:, 1] / (Hh - 1) - 1.0
+    return F.grid_sample(x, torch.stack((gx, gy), -1), padding_mode="border", mode="bicubic", align_corners=True)
+
+
+def torch_up2(flow):
+    return F.interpolate(flow, scale_factor=2, mode="bilinear", align_corners=True) * 2.0
 
 
 def timeit(fn, n=30):
@@ -53,13 +66,13 @@ for name, fD, Cf in (("config 2: recurrent-convunet (1 flow, 3-ch warp)", 0, 0),
         al.step(nn[0:1], flow, [nn[1:2]] if fD else [], [flow] if fD else [])
 
     def torch_ref():                                            # util/flow_utils.py on the GPU, as the reference runs it
-        up = warp_ref.upsample_factor_2(flow, 2)
-        outs = [warp_ref.warp(den, up, "bicubic")[0], n[1:2]]
+        up = torch_up2(flow)
+        outs = [torch_warp(den, up), n[1:2]]
         if fD:
-            outs.append(warp_ref.warp(n[2:3], up, "bicubic")[0])
+            outs.append(torch_warp(n[2:3], up))
         torch.cat(outs, 1)
         if Cf:
-            warp_ref.warp(feat.clone(), up, "bicubic")
+            torch_warp(feat.clone(), up)
 
     t_ours, t_ref = timeit(ours), timeit(torch_ref, n=10)
     t_online = timeit(lambda: flow_utils.compute_flows_from_denoised(den, packed[1:2]), n=3)

@@ -1,2 +1,1 @@
-mkdir -p gpurun_out
-timeout 600 python tools/time_sizes.py 2>&1 | tail -4
+timeout 600 python tools/time_groups.py 2>&1 | tail -9

@@ -174,25 +174,14 @@ struct rvdd_ctx {
     int prof_n = 0;
 };
 
-extern "C" int rvdd_create(rvdd_ctx **out)
+static int create_resources(rvdd_ctx *c)
 {
-    if (!out) return fail("rvdd_create: null out");
-    int ndev = 0;
-    cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e != cudaSuccess || ndev == 0) return fail("rvdd_create: no CUDA device (there is no CPU fallback)", e);
-    rvdd_ctx *c = new rvdd_ctx();
     CK(cudaGetDevice(&c->device));
     int coop = 0;
     CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
-    if (!coop) {
-        delete c;
-        return fail("rvdd_create: device lacks cooperative launch");
-    }
-    e = solver_max_ctas(&c->ctas_per_sm, &c->sms);
-    if (e != cudaSuccess || c->ctas_per_sm < 1) {
-        delete c;
-        return fail("rvdd_create: solver kernel does not fit on this device", e);
-    }
+    if (!coop) return fail("rvdd_create: device lacks cooperative launch");
+    const cudaError_t e = solver_max_ctas(&c->ctas_per_sm, &c->sms);
+    if (e != cudaSuccess || c->ctas_per_sm < 1) return fail("rvdd_create: solver kernel does not fit on this device", e);
     for (int i = 0; i < RING; i++) CK(cudaEventCreateWithFlags(&c->ring_ev[i], cudaEventDisableTiming));
     for (int i = 0; i < 2; i++) {
         CK(cudaEventCreateWithFlags(&c->slot_in[i], cudaEventDisableTiming));
@@ -204,6 +193,26 @@ extern "C" int rvdd_create(rvdd_ctx **out)
     CK(cudaStreamCreateWithFlags(&c->st_compute, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking));
+    return 0;
+}
+
+extern "C" int rvdd_destroy(rvdd_ctx *c);
+
+extern "C" int rvdd_create(rvdd_ctx **out)
+{
+    if (!out) return fail("rvdd_create: null out");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail("rvdd_create: no CUDA device (there is no CPU fallback)", e);
+    rvdd_ctx *c = new rvdd_ctx();
+    const int rc = create_resources(c);
+    if (rc) {
+        const std::string why = g_err;          // rvdd_destroy may overwrite the message
+        rvdd_destroy(c);                        // releases whatever was created
+        g_err = why;
+        return rc;
+    }
     *out = c;
     return 0;
 }

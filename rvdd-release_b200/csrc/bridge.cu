@@ -307,8 +307,12 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
 
     // ---- groups and workspace
     const int total_ctas = c->sms * c->ctas_per_sm;
-    // one group per pair while a group keeps at least 8 CTAs (48 warps); more pairs than that queue up behind the groups
-    int G = c->req_groups > 0 ? c->req_groups : (K < total_ctas / 8 ? K : total_ctas / 8);
+    // one group per pair while a group keeps a minimum of CTAs -- 8 (48 warps) for 1280x720 and larger, 4 / 2 for smaller
+    // frames, whose levels have too few row strips to feed more (measured at 640x360: 148 groups of 2 CTAs are 7 %
+    // faster than 37 groups of 8); more pairs than that queue up behind the groups
+    const long long npx = (long long)nx * ny;
+    const int min_ctas = npx >= 600000 ? 8 : (npx >= 300000 ? 4 : 2);
+    int G = c->req_groups > 0 ? c->req_groups : (K < total_ctas / min_ctas ? K : total_ctas / min_ctas);
     if (G < 1) G = 1;
     if (G > K) G = K;
     if (G > total_ctas) G = total_ctas;

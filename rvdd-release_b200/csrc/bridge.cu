@@ -288,6 +288,7 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
     if (npairs <= 0) return 0;
     if (!gray || !src || !tgt || !flow) return fail("rvdd_tvl1_flow_dev: null argument");
     if (nx < 4 || ny < 4 || (long long)nx * ny > (1LL << 30)) return fail("rvdd_tvl1_flow_dev: unsupported image size");
+    if (npairs > 32767) return fail("rvdd_tvl1_flow_dev: at most 32767 pairs per call (split the batch)");
     cudaStream_t st = (cudaStream_t)stream;
     rvdd_tvl1_params p = sanitize(params);
     Pyramid P;

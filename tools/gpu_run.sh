@@ -1,4 +1,2 @@
 mkdir -p gpurun_out
-python bench.py --noise clean > gpurun_out/v_clean.json 2> gpurun_out/v_clean.err
-python bench.py --noise iso12800 > gpurun_out/v_iso12800.json 2> gpurun_out/v_iso12800.err
-python bench.py --noise iso3200 --no-cpu-baseline > gpurun_out/v_iso3200.json 2> gpurun_out/v_iso3200.err
+python bench.py --steps 100 --warmup 5 --no-cpu-baseline > gpurun_out/x_long.json 2> gpurun_out/x_long.err

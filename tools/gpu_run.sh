@@ -1,2 +1,2 @@
-mkdir -p gpurun_out
-for i in 1 2 3; do python -m pytest tests -m gpu -q 2>&1 | grep -v Warning | tail -1; done
+python tools/time_single.py 2>&1 | tail -4 | cut -c1-40
+RVDD_BRIDGE_LIB=rvdd-release_b200/lib/libBridge_red.so python tools/time_single.py 2>&1 | tail -4 | cut -c1-40

@@ -34,7 +34,8 @@ extern "C" {
  *   u : caller-allocated 2*nx*ny floats; on return plane 0 = x-displacement, plane 1 = y-displacement, with
  *       I1(x + u) ~ I0(x).  Parameters are the hard-wired defaults of libBridge.cpp:27-36.
  * Buffers are neither retained nor modified (except u).  On failure u is left untouched and the error is
- * recorded (rvdd_last_error); the process is not killed. */
+ * recorded (rvdd_last_error); the process is not killed.  The call runs on the CUDA device current in the calling
+ * thread (one lazily created context per device) and is serialised by a mutex. */
 RVDD_API void tvl1flow(float *I0, float *I1, float *u, int nx, int ny);
 
 /* TV-L1 parameters (libBridge.cpp:27-36, tvl1flow_lib.c:343-359).  MAX_ITERATIONS=300, the presmoothing sigma
@@ -60,12 +61,18 @@ RVDD_API int rvdd_pyramid(int nx, int ny, const rvdd_tvl1_params *p, int *nxs, i
  * Context: owns the device workspace (pyramids, solver scratch, barrier words) so that no call allocates in
  * steady state -- the arena that replaces the reference's per-call xmalloc/free (tvl1flow_lib.c:110-129,
  * :364-401).  A context is bound to the CUDA device current at creation and must not be used from two threads
- * at once.  n_groups: how many frame pairs the persistent solver works on concurrently (0 = choose from the
+ * at once.  Calls on different streams are safe: the workspace is shared, so a call queued on another stream than
+ * the previous one first waits (on the device, cudaStreamWaitEvent) for that one's kernels.  n_groups: how many frame pairs the persistent solver works on concurrently (0 = choose from the
  * batch size). */
 typedef struct rvdd_ctx rvdd_ctx;
 RVDD_API int rvdd_create(rvdd_ctx **out);
 RVDD_API int rvdd_destroy(rvdd_ctx *ctx);
 RVDD_API int rvdd_set_groups(rvdd_ctx *ctx, int n_groups);
+/* Watchdog of the persistent solver: a group barrier that waits longer than `ticks` SM clock cycles (default 4e9, about
+ * 2 s; also settable with the environment variable RVDD_WATCHDOG_TICKS at context creation) makes the launch unwind.
+ * Raise it under time-slicing / MPS / a debugger.  When it fires, every flow of that call is overwritten with NaN on
+ * the device (visible without a synchronisation) and rvdd_solver_status / the host entry points report the error. */
+RVDD_API int rvdd_set_watchdog(rvdd_ctx *ctx, long long ticks);
 RVDD_API const char *rvdd_last_error(void);
 RVDD_API int rvdd_abi_version(void);
 

@@ -34,6 +34,7 @@ _SIGNATURES = {
     "rvdd_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "rvdd_destroy": (C.c_int, [C.c_void_p]),
     "rvdd_set_groups": (C.c_int, [C.c_void_p, C.c_int]),
+    "rvdd_set_watchdog": (C.c_int, [C.c_void_p, C.c_longlong]),
     "rvdd_last_error": (C.c_char_p, []),
     "rvdd_abi_version": (C.c_int, []),
     "rvdd_gray_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -123,6 +124,10 @@ class Bridge:
 
     def set_groups(self, n):
         self._ck(self.lib.rvdd_set_groups(self.ctx, int(n)))
+
+    def set_watchdog(self, ticks):
+        """Solver watchdog in SM clock ticks (default 4e9); a launch whose watchdog fires returns NaN flows."""
+        self._ck(self.lib.rvdd_set_watchdog(self.ctx, int(ticks)))
 
     # ------------------------------------------------------------------ geometry
     def pyramid(self, nx, ny, params=None):

@@ -3,9 +3,11 @@
 // `tvl1flow` symbol (libBridge.cpp:44) and the host-buffer end-to-end entry point.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <cmath>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -70,14 +72,16 @@ static rvdd_tvl1_params sanitize(const rvdd_tvl1_params *in)
 }
 
 // libBridge.cpp:131-138 (same C++ expression, so the same float/double overloads are picked) + zoom.c:22-34
-static void build_pyramid(int nx, int ny, rvdd_tvl1_params &p, Pyramid &P)
+// Returns false when the reference would use more scales than the workspace tables hold (RVDD_MAX_SCALES; only
+// reachable with a zoom factor close to 1): the caller reports an error instead of silently computing another pyramid.
+static bool build_pyramid(int nx, int ny, rvdd_tvl1_params &p, Pyramid &P)
 {
     float zfactor = p.zfactor;
     int nscales = p.nscales;
     const float N = 1 + log(hypot(nx, ny) / 16.0) / log(1 / zfactor);
     if (N < nscales) nscales = N;
     if (nscales < p.fscale) p.fscale = nscales;
-    if (nscales > RVDD_MAX_SCALES) nscales = RVDD_MAX_SCALES;
+    if (nscales > RVDD_MAX_SCALES) return false;
     if (nscales < 1) nscales = 1;
     p.nscales = nscales;
     P.S = nscales;
@@ -93,13 +97,17 @@ static void build_pyramid(int nx, int ny, rvdd_tvl1_params &p, Pyramid &P)
         off += ((long long)P.nx[s] * P.ny[s] + 3) & ~3LL;
     }
     P.total = off;
+    return true;
 }
 
 extern "C" int rvdd_pyramid(int nx, int ny, const rvdd_tvl1_params *params, int *nxs, int *nys)
 {
     rvdd_tvl1_params p = sanitize(params);
     Pyramid P;
-    build_pyramid(nx, ny, p, P);
+    if (!build_pyramid(nx, ny, p, P)) {
+        fail("rvdd_pyramid: more than RVDD_TRACE_SCALES scales (zfactor too close to 1)");
+        return -1;
+    }
     for (int s = 0; s < P.S; s++) {
         if (nxs) nxs[s] = P.nx[s];
         if (nys) nys[s] = P.ny[s];
@@ -172,6 +180,12 @@ struct rvdd_ctx {
     bool prof = false;
     std::vector<cudaEvent_t> prof_ev;   // begin/end pairs
     int prof_n = 0;
+    // The TV-L1 workspace (pyramids, solver scratch, barrier words, pointer table) is shared by every entry point: a call
+    // queued on another stream than the previous one first waits for that one's kernels (ws_ev).
+    cudaEvent_t ws_ev = nullptr;
+    cudaStream_t ws_stream = nullptr;
+    bool ws_used = false;
+    long long spin_limit = 4000000000LL;        // solver watchdog in clock64 ticks (~2 s at 2 GHz); rvdd_set_watchdog
 };
 
 static int create_resources(rvdd_ctx *c)
@@ -189,6 +203,11 @@ static int create_resources(rvdd_ctx *c)
         CK(cudaEventCreateWithFlags(&c->slot_done[i], cudaEventDisableTiming));
         CK(cudaMallocHost((void **)&c->slot_status_host[i], sizeof(int)));
         *c->slot_status_host[i] = 0;
+    }
+    CK(cudaEventCreateWithFlags(&c->ws_ev, cudaEventDisableTiming));
+    if (const char *env = getenv("RVDD_WATCHDOG_TICKS")) {
+        const long long v = atoll(env);
+        if (v > 0) c->spin_limit = v;
     }
     CK(cudaStreamCreateWithFlags(&c->st_compute, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking));
@@ -235,6 +254,7 @@ extern "C" int rvdd_destroy(rvdd_ctx *c)
         if (c->ring_host[i]) cudaFreeHost(c->ring_host[i]);
         if (c->ring_ev[i]) cudaEventDestroy(c->ring_ev[i]);
     }
+    if (c->ws_ev) cudaEventDestroy(c->ws_ev);
     for (cudaEvent_t ev : c->events) cudaEventDestroy(ev);
     for (cudaEvent_t ev : c->prof_ev) cudaEventDestroy(ev);
     if (c->st_compute) cudaStreamDestroy(c->st_compute);
@@ -249,6 +269,24 @@ extern "C" int rvdd_set_groups(rvdd_ctx *c, int n)
     if (!c) return fail("rvdd_set_groups: null context");
     c->req_groups = n < 0 ? 0 : n;
     return 0;
+}
+
+extern "C" int rvdd_set_watchdog(rvdd_ctx *c, long long ticks)
+{
+    if (!c) return fail("rvdd_set_watchdog: null context");
+    if (ticks <= 0) return fail("rvdd_set_watchdog: ticks must be positive");
+    c->spin_limit = ticks;
+    return 0;
+}
+
+// A solver launch whose watchdog fired unwinds early and leaves the flow buffer partly written: make that visible without
+// a host synchronisation by overwriting the whole result with NaN (every consumer then fails loudly instead of using
+// stale values).  One tiny launch per solver call; the threads of a healthy launch read one word and return.
+__global__ void poison_on_failure_kernel(const int *__restrict__ status, float *__restrict__ flow, long long n)
+{
+    if (*status == 0) return;
+    const float nan = __int_as_float(0x7fc00000);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) flow[i] = nan;
 }
 
 // ------------------------------------------------------------------------------------------------ TMA descriptors
@@ -292,7 +330,8 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
     cudaStream_t st = (cudaStream_t)stream;
     rvdd_tvl1_params p = sanitize(params);
     Pyramid P;
-    build_pyramid(nx, ny, p, P);
+    if (!build_pyramid(nx, ny, p, P))
+        return fail("rvdd_tvl1_flow_dev: the reference would use more than 16 scales for this zfactor (unsupported)");
     const int S = P.S, K = npairs;
     for (int k = 0; k < K; k++)
         if (src[k] < 0 || src[k] >= nframes || tgt[k] < 0 || tgt[k] >= nframes)
@@ -305,6 +344,9 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
     if (pre.size > nx || pre.size > ny) return fail("image smaller than the presmoothing kernel (mask.c:229)");
     for (int s = 0; s + 1 < S; s++)
         if (zoom.size > P.nx[s] || zoom.size > P.ny[s]) return fail("pyramid level smaller than the zoom kernel (mask.c:229)");
+
+    // ---- the shared workspace: order this call after the previous one if that ran on another stream
+    if (c->ws_used && c->ws_stream != st) CK(cudaStreamWaitEvent(st, c->ws_ev, 0));
 
     // ---- groups and workspace
     const int total_ctas = c->sms * c->ctas_per_sm;
@@ -408,7 +450,7 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
     }
     A.bar = bar; A.partials = partials; A.status = status;
     A.ngroups = G; A.ctas_per_group = C;
-    A.spin_limit = 4000000000LL;                             // ~2 s at 2 GHz
+    A.spin_limit = c->spin_limit;
     if (iters) CK(cudaMemsetAsync(iters, 0, sizeof(int) * (size_t)K * RVDD_TRACE_SCALES * p.nwarps, st));
     if (c->prof) {
         if ((int)c->prof_ev.size() < 2 * (c->prof_n + 1)) {
@@ -425,6 +467,11 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
         CK(cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st));
         c->prof_n++;
     }
+    poison_on_failure_kernel<<<c->sms, 256, 0, st>>>(status, flow, (long long)K * 2 * nx * ny);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ws_ev, st));
+    c->ws_stream = st;
+    c->ws_used = true;
     return 0;
 }
 
@@ -701,18 +748,25 @@ extern "C" int rvdd_flow_and_warp_host(rvdd_ctx *c, const float *frames, int nfr
 }
 
 // The reference symbol (libBridge.cpp:44): host float buffers, default parameters, planar (u, v) result.
+// One lazily created context per CUDA device: the call runs on whichever device is current in the calling thread.
 static std::mutex g_mu;
-static rvdd_ctx *g_ctx = nullptr;
+static std::map<int, rvdd_ctx *> g_ctxs;
 
 extern "C" void tvl1flow(float *I0, float *I1, float *u, int nx, int ny)
 {
     std::lock_guard<std::mutex> lock(g_mu);
-    if (!g_ctx && rvdd_create(&g_ctx)) {
-        fprintf(stderr, "libBridge(tvl1flow): %s\n", rvdd_last_error());
-        g_ctx = nullptr;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        fprintf(stderr, "libBridge(tvl1flow): no CUDA device (there is no CPU fallback)\n");
         return;
     }
-    rvdd_ctx *c = g_ctx;
+    rvdd_ctx *&slot = g_ctxs[dev];
+    if (!slot && rvdd_create(&slot)) {
+        fprintf(stderr, "libBridge(tvl1flow): %s\n", rvdd_last_error());
+        slot = nullptr;
+        return;
+    }
+    rvdd_ctx *c = slot;
     const size_t n = (size_t)nx * ny;
     cudaStream_t st = c->st_compute;
     auto bail = [&](const char *what, cudaError_t e) {

@@ -66,10 +66,11 @@ __device__ __forceinline__ bool group_sync(GroupCtx &g, int *s_flag)
         int dead = 0;
         unsigned spins = 0;
         while ((int)(ld_acquire_u32(g.bar) - g.target) < 0) {
-            if ((++spins & 1023u) == 0) {
-                if (*(volatile int *)g.status != 0) { dead = 1; break; }
+            if ((spins & 1023u) == 0) {      // the clock is looked at on the first unsuccessful poll, then every 1024
+                if (spins && *(volatile int *)g.status != 0) { dead = 1; break; }
                 if (clock64() - t0 > g.spin_limit) { atomicExch(g.status, 1); dead = 1; break; }
             }
+            ++spins;
         }
         if (!dead && *(volatile int *)g.status != 0) dead = 1;
         __threadfence();

@@ -82,3 +82,51 @@ def gray_pair(h, w, iso="iso3200", t=1, device="cpu", seed=1, noise_seed=0):
     seq = sequence(t + 1, h, w, iso, device, seed, noise_seed)
     g = seq.cpu().numpy().mean(axis=3, dtype=np.float32)
     return np.ascontiguousarray(g[t]), np.ascontiguousarray(g[t - 1])
+
+
+def exact_gray_pair(h, w, seed=7, noise=True):
+    """(I0, I1) float32 gray images of a noisy textured pair with ~2-4 px smooth motion, built ONLY from operations that
+    are bit-reproducible on every IEEE-754 machine (PCG64 integers, float64 + - * /, floor, abs, sqrt -- no sin / exp /
+    log, whose last bit depends on the libm / SIMD path of the host).  Used for golden vectors of geometries too large to
+    run the oracle next to the GPU test (tests/golden/large_tvl1_2160x3840_exact.npz): the inputs are regenerated on the GPU
+    box and must hash to the committed value."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    y, x = np.meshgrid(np.arange(h, dtype=np.float64), np.arange(w, dtype=np.float64), indexing="ij")
+
+    def tri(v):                                         # triangle wave in [0, 1], period 2
+        return np.abs(v - 2.0 * np.floor(v / 2.0) - 1.0)
+
+    def value_noise(cy, cx, cell, grid):
+        gy, gx = cy / cell, cx / cell
+        iy, ix = np.floor(gy), np.floor(gx)
+        fy, fx = gy - iy, gx - ix
+        iy = np.clip(iy.astype(np.int64), 0, grid.shape[0] - 2)
+        ix = np.clip(ix.astype(np.int64), 0, grid.shape[1] - 2)
+        a, b, c, d = grid[iy, ix], grid[iy, ix + 1], grid[iy + 1, ix], grid[iy + 1, ix + 1]
+        top = a + fx * (b - a)
+        bot = c + fx * (d - c)
+        return top + fy * (bot - top)
+
+    octaves = [(64.0, 1.0), (16.0, 0.5), (6.0, 0.25)]
+    grids = [rng.integers(0, 1024, size=(int(h // c) + 12, int(w // c) + 12)).astype(np.float64) for c, _ in octaves]
+    amp_sum = sum(a for _, a in octaves)
+
+    def frame(moved):
+        cy, cx = y + 16.0, x + 16.0
+        if moved:                                       # the source frame: texture seen through a smooth displacement
+            cx = cx - (2.25 + 1.5 * tri(y / 97.0))
+            cy = cy - (-1.5 + 1.0 * tri(x / 131.0))
+        t = np.zeros((h, w), np.float64)
+        for (cell, a), g in zip(octaves, grids):
+            t = t + a * value_noise(cy, cx, cell, g)
+        return 266.0 + t / (1023.0 * amp_sum) * (3610.0 - 266.0)
+
+    out = []
+    for moved in (False, True):
+        raw = frame(moved)
+        if noise:                                       # ISO-3200-like heteroscedastic noise after the mean of 4 channels
+            var = np.maximum(8.0034 * raw - 2043.51144, 0.0) / 4.0
+            s = rng.integers(0, 65536, size=(4, h, w)).astype(np.float64).sum(axis=0) - 2.0 * 65535.0
+            raw = raw + np.sqrt(var) * (s / 37837.0)    # sum of 4 uniforms: standard deviation 65536 / sqrt(3) = 37837
+        out.append(np.ascontiguousarray(raw.astype(np.float32)))
+    return out[0], out[1]

@@ -136,3 +136,52 @@ def test_recurrent_convunet_feat_future_psnr_within_0p02_db(bridge):
     assert float((den_ours - golden).abs().max()) <= max(2e-3, 2.0 * noise), (float((den_ours - golden).abs().max()), noise)
     assert float((den_ours - den_gref).abs().max()) <= max(2e-3, 2.0 * noise)
     assert np.max(np.abs(psnr_ours - psnr_gref)) <= 0.01
+
+
+def test_frame_aligner_depth2_matches_reference_loop(bridge):
+    """model_patch_depth 3 (two previous frames, D = 2) + one future frame + feature recurrence: FrameAligner against the
+    reference's alignment block (models/recurrent_model.py:268-345) restated with the oracle warp, with a stand-in
+    'network' (any deterministic function of the two inputs will do -- the denoiser is out of scope)."""
+    from rvdd_release_b200.recurrent_align import FrameAligner
+    B, C, H, W, D, fD, Cf, T = 2, 3, 48, 64, 2, 1, 8, 4
+    g = torch.Generator().manual_seed(3)
+    n = torch.randn(B, (D + T + fD) * C, H, W, generator=g)                     # D initial + T processed + fD lookahead
+    flow = 2.0 * torch.randn(B, T, D + fD, 2, H // 2, W // 2, generator=g)      # half-resolution flows, as the dataset's
+
+    def fake_net(netinput, featinput):
+        den = netinput.view(netinput.shape[0], -1, C, H, W).mean(1) + 0.1 * featinput[:, :C]
+        feat = 0.5 * featinput[:, :Cf] + netinput[:, :1]
+        return den, feat
+
+    # reference loop on the CPU (oracle warp; torch.cat / clone exactly as the reference does)
+    lastden = n[:, :D * C]
+    lastfeat = torch.zeros(B, D * Cf, H, W)
+    ref_out = []
+    for a in range(T):
+        up = warp_ref.upsample_factor_2(flow[:, a], multiply_by=2)
+        featinput = lastfeat.clone()
+        netinput = None
+        for b in range(D):
+            warped = warp_ref.warp(lastden[:, b * C:(b + 1) * C].contiguous(), up[:, b], "bicubic")[0]
+            featinput[:, b * Cf:(b + 1) * Cf] = warp_ref.warp(featinput[:, b * Cf:(b + 1) * Cf].clone(), up[:, b], "bicubic")[0]
+            netinput = warped if netinput is None else torch.cat((netinput, warped), 1)
+        netinput = torch.cat((netinput, n[:, (a + D) * C:(a + D + 1) * C]), 1)
+        for b in range(fD):
+            fr = n[:, (a + D + 1 + b) * C:(a + D + 2 + b) * C].contiguous()
+            netinput = torch.cat((netinput, warp_ref.warp(fr, up[:, D + b], "bicubic")[0]), 1)
+        den, feat = fake_net(netinput, featinput)
+        ref_out.append(den)
+        lastden = torch.cat((lastden[:, C:], den.clone()), 1)
+        lastfeat = torch.cat((lastfeat[:, Cf:], feat), 1)
+
+    al = FrameAligner(depth=D, future_depth=fD, feature_channels=Cf, predemosaic=False)
+    nc, fc = n.cuda(), flow.cuda()
+    al.reset(nc[:, :D * C])
+    for a in range(T):
+        netinput, featinput = al.step(nc[:, (a + D) * C:(a + D + 1) * C], fc[:, a, :D],
+                                      [nc[:, (a + D + 1 + b) * C:(a + D + 2 + b) * C] for b in range(fD)],
+                                      [fc[:, a, D + b] for b in range(fD)])
+        den, feat = fake_net(netinput, featinput)
+        al.update(den.clone(), feat.clone())
+        err = float((den.cpu() - ref_out[a]).abs().max() / ref_out[a].abs().max())
+        assert err <= 5e-4, (a, err)

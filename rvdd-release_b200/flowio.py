@@ -28,7 +28,7 @@ def write_tif(path, arr):
     if a.ndim == 2:
         a = a[:, :, None]
     h, w, c = a.shape
-    data = a.tobytes()
+    data = memoryview(a).cast("B")          # no copy: the pixel bytes go to the file straight from the array
     entries = [
         (256, 4, 1, w), (257, 4, 1, h),                     # ImageWidth, ImageLength
         (258, 3, c, [32] * c),                              # BitsPerSample
@@ -97,6 +97,56 @@ def _lzw_decode(buf, expected):
             if len(out) >= expected:
                 return bytes(out[:expected])
     return bytes(out[:expected])
+
+
+def read_tif_into(path, out):
+    """Fast path of the precompute readers: if ``path`` is an uncompressed little-endian float32 TIFF whose strips are
+    stored back to back (what ``write_tif`` and libtiff write), read its pixels STRAIGHT into ``out`` ((h, w, c)
+    float32, C-contiguous -- e.g. a slice of a pinned staging buffer) with one ``readinto`` and return True.  Anything
+    else returns False and the caller falls back to ``read_image``."""
+    with open(path, "rb") as f:
+        head = f.read(8)
+        if head[:4] != b"II*\0":
+            return False
+        off = struct.unpack("<I", head[4:8])[0]
+        f.seek(off)
+        n = struct.unpack("<H", f.read(2))[0]
+        ifd = f.read(12 * n)
+        tags = {}
+        for i in range(n):
+            tag, typ, cnt, val = struct.unpack("<HHII", ifd[12 * i:12 * i + 12])
+            if typ == 3 and cnt == 1:
+                val &= 0xffff
+            tags[tag] = (typ, cnt, val)
+
+        def first(tag, default):
+            """first value of a SHORT / LONG tag (values that do not fit the 4-byte field are fetched)"""
+            if tag not in tags:
+                return default
+            typ, cnt, val = tags[tag]
+            size = _TYPES.get(typ, ("B", 1))[1]
+            if size * cnt <= 4:
+                return val & 0xffff if typ == 3 else val
+            f.seek(val)
+            return struct.unpack("<" + _TYPES[typ][0], f.read(size))[0]
+
+        w, h, c = first(256, 0), first(257, 0), first(277, 1)
+        if (first(259, 1) != 1 or first(339, 1) != 3 or first(258, 1) != 32 or (c > 1 and first(284, 1) != 1)
+                or first(317, 1) != 1 or out.shape != (h, w, c) or out.dtype != np.float32 or not out.flags["C_CONTIGUOUS"]):
+            return False
+        typ, cnt, val = tags[273]
+        if cnt != 1:                                        # several strips: accept only if they are contiguous
+            fmt, size = _TYPES[typ]
+            f.seek(val)
+            offs = struct.unpack("<%d%s" % (cnt, fmt), f.read(size * cnt))
+            t2, c2, v2 = tags[279]
+            f.seek(v2)
+            cnts = struct.unpack("<%d%s" % (c2, _TYPES[t2][0]), f.read(_TYPES[t2][1] * c2))
+            if any(offs[i] + cnts[i] != offs[i + 1] for i in range(cnt - 1)):
+                return False
+            val = offs[0]
+        f.seek(val)
+        return f.readinto(memoryview(out).cast("B")) == out.nbytes
 
 
 def read_tif(path):

@@ -45,13 +45,16 @@ def _code(path):
 
 
 def plan_video(frame_paths, flow_dir, warp_dir=None, patch_depth=2, future_patch_depth=0):
-    """The pairs of one video that still need work -> list of dicts(src, tgt, flow_file, warp_file)."""
+    """The pairs of one video that still need work -> list of dicts(src, tgt, flow_file, warp_file, need_flow), ordered
+    by frame position so that a batch's past and future pairs share their frames (one upload for both)."""
     todo = []
     for s, t in video_pairs(len(frame_paths), patch_depth, future_patch_depth):
         ff = warpedimagefile(flow_dir, _code(frame_paths[s]), _code(frame_paths[t]))
         wf = warpedimagefile(warp_dir, _code(frame_paths[s]), _code(frame_paths[t])) if warp_dir else None
-        if not os.path.isfile(ff) or (wf and not os.path.isfile(wf)):
-            todo.append(dict(src=s, tgt=t, flow_file=ff, warp_file=wf))
+        need_flow = not os.path.isfile(ff)
+        if need_flow or (wf and not os.path.isfile(wf)):
+            todo.append(dict(src=s, tgt=t, flow_file=ff, warp_file=wf, need_flow=need_flow))
+    todo.sort(key=lambda p: (min(p["src"], p["tgt"]), p["src"] > p["tgt"]))
     return todo
 
 
@@ -62,8 +65,29 @@ def gpu_compute(frames, src, tgt, want_warp):
     return flow.numpy(), (warped.numpy() if want_warp else None)
 
 
+def warp_only(frame, flow):
+    """A pair whose flow file exists but whose warped file is missing: warp with the CACHED flow, exactly as
+    base_dataset.py:182-185 does (the cache may have been written by the reference or with other parameters)."""
+    from . import flow_utils
+    return flow_utils.single_warp(frame, flow)
+
+
+def _split_cached(todo, frame_paths, written, warp=warp_only):
+    """Handle the warp-only pairs of a plan on the spot and return the pairs that need a flow."""
+    rest = []
+    for p in todo:
+        if p["need_flow"]:
+            rest.append(p)
+            continue
+        flow = flowio.read_tif(p["flow_file"]).astype(np.float32)
+        img1 = flowio.read_image(frame_paths[p["src"]]).astype(np.float32)
+        flowio.write_tif(p["warp_file"], warp(img1, flow))                                    # base_dataset.py:189
+        written.append(p["warp_file"])
+    return rest
+
+
 def precompute_video(frame_paths, flow_dir, warp_dir=None, patch_depth=2, future_patch_depth=0, compute=gpu_compute,
-                     max_pairs_per_batch=64):
+                     max_pairs_per_batch=64, warp=warp_only):
     """Create the missing flow (and optionally warped) files of one video.  Returns the files written."""
     todo = plan_video(frame_paths, flow_dir, warp_dir, patch_depth, future_patch_depth)
     if not todo:
@@ -72,6 +96,7 @@ def precompute_video(frame_paths, flow_dir, warp_dir=None, patch_depth=2, future
     if warp_dir:
         os.makedirs(warp_dir, exist_ok=True)
     written = []
+    todo = _split_cached(todo, frame_paths, written, warp)
     for b0 in range(0, len(todo), max_pairs_per_batch):
         batch = todo[b0:b0 + max_pairs_per_batch]
         used = sorted({p["src"] for p in batch} | {p["tgt"] for p in batch})
@@ -81,76 +106,154 @@ def precompute_video(frame_paths, flow_dir, warp_dir=None, patch_depth=2, future
         tgt = [local[p["tgt"]] for p in batch]
         flow, warped = compute(frames, src, tgt, warp_dir is not None)
         for k, p in enumerate(batch):
-            if not os.path.isfile(p["flow_file"]):
-                flowio.write_tif(p["flow_file"], flow[k])                                     # base_dataset.py:180
-                written.append(p["flow_file"])
+            flowio.write_tif(p["flow_file"], flow[k])                                         # base_dataset.py:180
+            written.append(p["flow_file"])
             if p["warp_file"] and not os.path.isfile(p["warp_file"]):
                 flowio.write_tif(p["warp_file"], warped[k])                                   # base_dataset.py:189
                 written.append(p["warp_file"])
     return written
 
 
+class _HostSet:
+    """One set of pinned host buffers (frames in, flows out, warped frames out).  There are NHOST of them per process,
+    each sized for the largest batch seen so far; a bigger batch frees the old buffers before allocating new ones, so
+    the pinned footprint is bounded by NHOST x the largest batch, whatever the mix of video lengths."""
+
+    def __init__(self, torch):
+        self.t = torch
+        self.pin = torch.cuda.is_available()               # (host-logic tests drive the pipeline with a stand-in bridge)
+        self.frames = self.flow = self.warp = None
+        self.writes = []                                   # futures of the files being written from this set
+
+    def _fit(self, name, shape):
+        n = int(np.prod(shape))
+        buf = getattr(self, name)
+        if buf is None or buf.numel() < n:
+            setattr(self, name, None)                      # release the old pinned block first
+            del buf
+            buf = self.t.empty(n, dtype=self.t.float32)
+            setattr(self, name, buf.pin_memory() if self.pin else buf)
+
+    def shape(self, nfr, h, w, c, npairs, want_warp):
+        self._fit("frames", (nfr, h, w, c))
+        self._fit("flow", (npairs, h, w, 2))
+        if want_warp:
+            self._fit("warp", (npairs, h, w, c))
+        return (self.frames[:nfr * h * w * c].view(nfr, h, w, c), self.flow[:npairs * h * w * 2].view(npairs, h, w, 2),
+                self.warp[:npairs * h * w * c].view(npairs, h, w, c) if want_warp else None)
+
+    def pinned_bytes(self):
+        return 4 * sum(b.numel() for b in (self.frames, self.flow, self.warp) if b is not None)
+
+
 class _PipelinedGPU:
-    """Feeds batches to libBridge.so through its two staging slots (rvdd_flow_and_warp_host_submit / _wait): while
-    one batch is on the GPU the previous one is written to disk and the next one is read and uploaded."""
+    """The offline precompute as a pipeline: a pool of reader threads decodes the frame files of
+    batch i+1 straight into pinned memory while the GPU (libBridge.so's two staging slots,
+    rvdd_flow_and_warp_host_submit / _wait: upload, kernels and download of consecutive batches overlap on three streams)
+    works on batches i and i-1, and a pool of writer threads stores the flows of batch i-2.  The submitting thread only
+    schedules; file I/O never sits between two GPU submissions."""
+    NHOST = 4
 
-    def __init__(self):
+    def __init__(self, readers=None, writers=None, bridge=None):
         import torch
-        from . import bridge
-        self.torch, self.br = torch, bridge.default_bridge()
-        self.jobs = [None, None]
+        from concurrent.futures import ThreadPoolExecutor
+        if bridge is None:
+            from . import bridge as _b
+            bridge = _b.default_bridge()
+        self.torch, self.br = torch, bridge
+        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 4)
+        self.readers = ThreadPoolExecutor(readers or max(2, min(8, ncpu // 2)), thread_name_prefix="rvdd-read")
+        self.writers = ThreadPoolExecutor(writers or max(2, min(8, ncpu // 2)), thread_name_prefix="rvdd-write")
+        self.sets = [_HostSet(torch) for _ in range(self.NHOST)]
         self.k = 0
+        self.reading = None                                # (job, read futures) of the batch being read
+        self.on_gpu = [None, None]                         # job per staging slot
+        self.nsub = 0
         self.written = []
+        self.stats = dict(batches=0, pairs=0, frames_read=0, bytes_read=0, bytes_written=0)
 
-    def _buffers(self, slot, nfr, h, w, c, npairs, want_warp):
-        t = self.torch
-        key = (nfr, h, w, c, npairs, want_warp)
-        cache = getattr(self, "_cache", None) or {}
-        self._cache = cache
-        if (slot, key) not in cache:
-            cache[(slot, key)] = (t.empty((nfr, h, w, c), dtype=t.float32).pin_memory(),
-                                  t.empty((npairs, h, w, 2), dtype=t.float32).pin_memory(),
-                                  t.empty((npairs, h, w, c), dtype=t.float32).pin_memory() if want_warp else None)
-        return cache[(slot, key)]
+    # ---- stage 1: read
+    def _start_read(self, frame_paths, batch, want_warp):
+        hs = self.sets[self.k % self.NHOST]
+        self.k += 1
+        for f in hs.writes:                                # the files of the batch that used this set 4 batches ago
+            f.result()
+        hs.writes = []
+        used = sorted({p["src"] for p in batch} | {p["tgt"] for p in batch})
+        local = {f: i for i, f in enumerate(used)}
+        first = flowio.read_image(frame_paths[used[0]])
+        h, w, c = first.shape
+        frames, flow, warped = hs.shape(len(used), h, w, c, len(batch), want_warp)
+        fr_np = frames.numpy()
+        fr_np[0] = first
 
-    def _finish(self, slot):
-        job = self.jobs[slot]
+        def load(i, path):                                 # pixels straight into pinned memory (one readinto) ...
+            if not flowio.read_tif_into(path, fr_np[i]):
+                fr_np[i] = flowio.read_image(path)         # ... or decode + float32 conversion for other formats
+
+        futs = [self.readers.submit(load, i, frame_paths[f]) for i, f in enumerate(used[1:], 1)]
+        self.stats["frames_read"] += len(used)
+        self.stats["bytes_read"] += frames.numel() * 4
+        job = dict(hs=hs, batch=batch, frames=frames, flow=flow, warped=warped,
+                   src=[local[p["src"]] for p in batch], tgt=[local[p["tgt"]] for p in batch])
+        return job, futs
+
+    # ---- stage 2: GPU
+    def _submit(self, job, futs):
+        for f in futs:
+            f.result()                                     # frames of this batch are in pinned memory
+        slot = self.nsub & 1
+        self.nsub += 1
+        self._retire(slot)                                 # the batch submitted two steps ago on this slot
+        self.br.submit_host(slot, job["frames"], job["src"], job["tgt"], job["flow"], job["warped"])
+        self.on_gpu[slot] = job
+
+    # ---- stage 3: write
+    def _retire(self, slot):
+        job = self.on_gpu[slot]
         if job is None:
             return
         self.br.wait_host(slot)
-        batch, flow, warped = job
-        for k, p in enumerate(batch):
-            if not os.path.isfile(p["flow_file"]):
-                flowio.write_tif(p["flow_file"], flow[k].numpy())
-                self.written.append(p["flow_file"])
+        self.on_gpu[slot] = None
+        flow, warped = job["flow"].numpy(), (job["warped"].numpy() if job["warped"] is not None else None)
+        for k, p in enumerate(job["batch"]):
+            job["hs"].writes.append(self.writers.submit(flowio.write_tif, p["flow_file"], flow[k]))
+            self.written.append(p["flow_file"])
+            self.stats["bytes_written"] += flow[k].nbytes
             if p["warp_file"] and not os.path.isfile(p["warp_file"]):
-                flowio.write_tif(p["warp_file"], warped[k].numpy())
+                job["hs"].writes.append(self.writers.submit(flowio.write_tif, p["warp_file"], warped[k]))
                 self.written.append(p["warp_file"])
-        self.jobs[slot] = None
+                self.stats["bytes_written"] += warped[k].nbytes
+        self.stats["batches"] += 1
+        self.stats["pairs"] += len(job["batch"])
 
     def submit(self, frame_paths, batch, want_warp):
-        slot = self.k & 1
-        self.k += 1
-        self._finish(slot)                                  # this slot's previous batch: wait + write its files
-        used = sorted({p["src"] for p in batch} | {p["tgt"] for p in batch})
-        local = {f: i for i, f in enumerate(used)}
-        first = flowio.read_image(frame_paths[used[0]]).astype(np.float32)
-        h, w, c = first.shape
-        frames, flow, warped = self._buffers(slot, len(used), h, w, c, len(batch), want_warp)
-        frames[0].copy_(self.torch.from_numpy(first))
-        for i, f in enumerate(used[1:], 1):
-            frames[i].copy_(self.torch.from_numpy(flowio.read_image(frame_paths[f]).astype(np.float32)))
-        self.br.submit_host(slot, frames, [local[p["src"]] for p in batch], [local[p["tgt"]] for p in batch], flow, warped)
-        self.jobs[slot] = (batch, flow, warped)
+        nxt = self._start_read(frame_paths, batch, want_warp)      # batch i+1 starts reading ...
+        if self.reading is not None:
+            self._submit(*self.reading)                            # ... while batch i goes to the GPU
+        self.reading = nxt
 
     def drain(self):
-        self._finish(0)
-        self._finish(1)
+        if self.reading is not None:
+            self._submit(*self.reading)
+            self.reading = None
+        self._retire(self.nsub & 1)                                # older slot first
+        self._retire((self.nsub & 1) ^ 1)
+        for hs in self.sets:
+            for f in hs.writes:
+                f.result()
+            hs.writes = []
+        self.stats["pinned_bytes"] = sum(hs.pinned_bytes() for hs in self.sets)
         return self.written
+
+    def close(self):
+        self.readers.shutdown()
+        self.writers.shutdown()
 
 
 def precompute_dataset(videos, flow_root, warp_root=None, patch_depth=2, future_patch_depth=0, rank=0, world=1,
-                       compute=None, gather=None, max_pairs_per_batch=64):
+                       compute=None, gather=None, max_pairs_per_batch=64, readers=None, writers=None, stats=None,
+                       bridge=None):
     """``videos``: list of (name, [frame paths]).  Rank ``rank`` of ``world`` handles its round-robin shard.
 
     With ``compute=None`` the batches go through the GPU pipeline (upload / solve / download + file writing overlap
@@ -159,7 +262,7 @@ def precompute_dataset(videos, flow_root, warp_root=None, patch_depth=2, future_
     torch.distributed that is ``all_gather_object``; it is the only communication of the whole job."""
     mine = shard(videos, rank, world)
     written = []
-    pipe = _PipelinedGPU() if compute is None else None
+    pipe = _PipelinedGPU(readers, writers, bridge) if compute is None else None
     for name, paths in mine:
         flow_dir = os.path.join(flow_root, name)
         warp_dir = os.path.join(warp_root, name) if warp_root else None
@@ -171,10 +274,14 @@ def precompute_dataset(videos, flow_root, warp_root=None, patch_depth=2, future_
             os.makedirs(flow_dir, exist_ok=True)
             if warp_dir:
                 os.makedirs(warp_dir, exist_ok=True)
+            todo = _split_cached(todo, paths, written)
         for b0 in range(0, len(todo), max_pairs_per_batch):
             pipe.submit(paths, todo[b0:b0 + max_pairs_per_batch], warp_dir is not None)
     if pipe is not None:
         written += pipe.drain()
+        pipe.close()
+        if stats is not None:
+            stats.update(pipe.stats)
     if gather is not None:
         return [f for part in gather(written) for f in part]
     return written

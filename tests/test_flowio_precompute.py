@@ -125,3 +125,129 @@ def test_two_rank_sharding_over_gloo(tmp_path):
     assert precompute.shard(list(range(5)), 0, 2) == [0, 2, 4] and precompute.shard(list(range(5)), 1, 2) == [1, 3]
     flow_root = str(tmp_path / "flow")
     assert sum(len(os.listdir(os.path.join(flow_root, v))) for v, _ in videos) == 30
+
+
+def test_read_tif_into_fast_path_and_fallback(tmp_path):
+    rng = np.random.RandomState(3)
+    a = rng.randn(19, 23, 4).astype(np.float32)
+    p = str(tmp_path / "a.tif")
+    flowio.write_tif(p, a)
+    out = np.zeros((19, 23, 4), np.float32)
+    assert flowio.read_tif_into(p, out) and np.array_equal(out, a)
+    assert not flowio.read_tif_into(p, np.zeros((19, 23, 3), np.float32))            # wrong shape -> caller falls back
+    raw = bytearray(open(p, "rb").read())
+    ifd = int.from_bytes(raw[4:8], "little")
+    for i in range(int.from_bytes(raw[ifd:ifd + 2], "little")):
+        e = ifd + 2 + 12 * i
+        if int.from_bytes(raw[e:e + 2], "little") == 259:                              # Compression := LZW
+            raw[e + 8:e + 10] = (5).to_bytes(2, "little")
+    q = str(tmp_path / "marked_lzw.tif")
+    open(q, "wb").write(raw)
+    assert not flowio.read_tif_into(q, np.zeros((19, 23, 4), np.float32))            # compressed -> caller falls back
+    cv2 = pytest.importorskip("cv2")
+    strips = str(tmp_path / "strips.tif")
+    assert cv2.imwrite(strips, a[:, :, 0], [cv2.IMWRITE_TIFF_COMPRESSION, 1, cv2.IMWRITE_TIFF_ROWSPERSTRIP, 4])
+    out1 = np.zeros((19, 23, 1), np.float32)
+    assert flowio.read_tif_into(strips, out1) and np.array_equal(out1[:, :, 0], a[:, :, 0])   # libtiff's multi-strip layout
+
+
+def test_plan_orders_past_and_future_pairs_by_frame(tmp_path):
+    videos = _make_dataset(str(tmp_path), nvid=1, nfr=5)
+    todo = precompute.plan_video(videos[0][1], str(tmp_path / "flow" / "vid00"), None, 2, 1)
+    assert [(p["src"], p["tgt"]) for p in todo] == [(0, 1), (1, 0), (1, 2), (2, 1), (2, 3), (3, 2), (3, 4), (4, 3)]
+    assert all(p["need_flow"] for p in todo)
+
+
+def test_cached_flow_is_reused_for_a_missing_warp(tmp_path):
+    """base_dataset.py:182-185: flow file present, warped file missing -> warp with the CACHED flow, no recomputation."""
+    videos = _make_dataset(str(tmp_path), nvid=1, nfr=3)
+    flow_root, warp_root = str(tmp_path / "flow"), str(tmp_path / "warped")
+    precompute.precompute_dataset(videos, flow_root, None, 2, 0, compute=_fake_compute)
+    marker = np.full((6, 8, 2), 7.0, np.float32)
+    flowio.write_tif(os.path.join(flow_root, "vid00", "0000_0001.tif"), marker)       # a cache written by someone else
+    calls = []
+
+    def fake_warp(img, flow):
+        calls.append(float(flow[0, 0, 0]))
+        return img + flow[:, :, :1]
+
+    def no_compute(*a):
+        raise AssertionError("the flow must not be recomputed")
+
+    os.makedirs(os.path.join(warp_root, "vid00"))
+    files = precompute.precompute_video(videos[0][1], os.path.join(flow_root, "vid00"), os.path.join(warp_root, "vid00"),
+                                        2, 0, compute=no_compute, warp=fake_warp)
+    assert len(files) == 2 and calls[0] == 7.0
+    w = flowio.read_tif(os.path.join(warp_root, "vid00", "0000_0001.tif"))
+    assert w[0, 0, 0] == 0.0 + 7.0
+    assert np.array_equal(flowio.read_tif(os.path.join(flow_root, "vid00", "0000_0001.tif")), marker)
+
+
+class _FakeBridge:
+    """Stands in for libBridge.so's two staging slots: `submit_host` computes on a worker thread, `wait_host` joins it --
+    so the pipeline's overlap logic (reads ahead, deferred writes, buffer reuse) runs without a GPU."""
+
+    def __init__(self):
+        import threading
+        self.threading, self.jobs, self.order = threading, [None, None], []
+
+    def submit_host(self, slot, frames, src, tgt, flow_out, warped_out=None, params=None):
+        assert self.jobs[slot] is None, "slot submitted twice without a wait"
+
+        def work():
+            f, w = _fake_compute(frames.numpy(), src, tgt, warped_out is not None)
+            flow_out.numpy()[...] = f
+            if warped_out is not None:
+                warped_out.numpy()[...] = w
+
+        t = self.threading.Thread(target=work)
+        t.start()
+        self.jobs[slot] = t
+        self.order.append(("submit", slot))
+
+    def wait_host(self, slot):
+        if self.jobs[slot] is not None:
+            self.jobs[slot].join()
+            self.jobs[slot] = None
+        self.order.append(("wait", slot))
+
+
+def test_pipelined_driver_with_reader_and_writer_pools(tmp_path):
+    """The GPU path's pipeline (reader pool -> staging slots -> writer pool) against the synchronous driver: same files,
+    same contents, for videos of different lengths (ragged tail batches) and a batch size that splits videos."""
+    root = str(tmp_path)
+    videos = []
+    for v, nfr in enumerate((7, 3, 12, 2, 5)):
+        d = os.path.join(root, "noisy", "vid%02d" % v)
+        os.makedirs(d)
+        paths = []
+        for f in range(nfr):
+            p = os.path.join(d, "%04d.tif" % f)
+            flowio.write_tif(p, np.full((6, 8, 4), 100 * v + f, np.float32))
+            paths.append(p)
+        videos.append(("vid%02d" % v, paths))
+    ref_root, pipe_root = os.path.join(root, "flow_ref"), os.path.join(root, "flow_pipe")
+    ref_files = precompute.precompute_dataset(videos, ref_root, os.path.join(root, "w_ref"), 2, 1, compute=_fake_compute,
+                                              max_pairs_per_batch=5)
+    stats = {}
+    fb = _FakeBridge()
+    files = precompute.precompute_dataset(videos, pipe_root, os.path.join(root, "w_pipe"), 2, 1, max_pairs_per_batch=5,
+                                          readers=3, writers=3, stats=stats, bridge=fb)
+    rel = lambda fs, base: sorted(os.path.relpath(f, root).replace(base, "X") for f in fs)
+    assert rel(files, "_pipe") == rel(ref_files, "_ref") and len(files) == 2 * 2 * (6 + 2 + 11 + 1 + 4)
+    for f in ref_files:
+        g = f.replace("_ref", "_pipe")
+        assert np.array_equal(flowio.read_tif(f), flowio.read_tif(g)), g
+    assert stats["pairs"] == 48 and stats["batches"] >= 10 and stats["pinned_bytes"] > 0
+    # pinned footprint is bounded by NHOST x the largest batch (6 frames + 5 flows + 5 warped frames of 6x8 pixels)
+    assert stats["pinned_bytes"] <= 4 * 4 * (6 * 6 * 8 * 4 + 5 * 6 * 8 * 2 + 5 * 6 * 8 * 4)
+    # a slot is always waited for before it is submitted again
+    busy = [False, False]
+    for what, slot in fb.order:
+        if what == "submit":
+            assert not busy[slot]
+            busy[slot] = True
+        else:
+            busy[slot] = False
+    # resume: nothing left
+    assert precompute.precompute_dataset(videos, pipe_root, os.path.join(root, "w_pipe"), 2, 1, bridge=fb) == []

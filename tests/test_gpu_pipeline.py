@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import warp_ref
 from rvdd_release_b200 import flow_utils, synth
 
 pytestmark = pytest.mark.gpu

@@ -27,10 +27,11 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
-def needs_build():
-    if not os.path.exists(LIB):
+def needs_build(lib=None):
+    lib = lib or LIB
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "rvdd_bridge.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
@@ -41,8 +42,10 @@ def build_lib(force=False, verbose=False, variant=None, defines=()):
     variant/defines build an experimental lib/libBridge_<variant>.so with extra -D macros (tuning runs only; select
     it at run time with RVDD_BRIDGE_LIB)."""
     if variant:
-        return _build(os.path.join(PKG, "lib", "libBridge_%s.so" % variant), os.path.join(PKG, "lib", "obj_" + variant),
-                      verbose, ["-D" + d for d in defines], install=False)
+        vlib = os.path.join(PKG, "lib", "libBridge_%s.so" % variant)
+        if not force and os.path.exists(vlib) and not needs_build(vlib):
+            return vlib
+        return _build(vlib, os.path.join(PKG, "lib", "obj_" + variant), verbose, ["-D" + d for d in defines], install=False)
     if not force and not needs_build():
         return LIB
     return _build(LIB, os.path.join(PKG, "lib", "obj"), verbose, [], install=True)

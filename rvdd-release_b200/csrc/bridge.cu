@@ -186,6 +186,7 @@ struct rvdd_ctx {
     cudaStream_t ws_stream = nullptr;
     bool ws_used = false;
     long long spin_limit = 4000000000LL;        // solver watchdog in clock64 ticks (~2 s at 2 GHz); rvdd_set_watchdog
+    int fuse_min_px = 0, fuse_first = 1;        // two-iterations-per-pass policy of the solver (RVDD_FUSE_MIN_PX / _FIRST)
 };
 
 static int create_resources(rvdd_ctx *c)
@@ -209,6 +210,8 @@ static int create_resources(rvdd_ctx *c)
         const long long v = atoll(env);
         if (v > 0) c->spin_limit = v;
     }
+    if (const char *env = getenv("RVDD_FUSE_MIN_PX")) c->fuse_min_px = atoi(env);     // tuning / A-B runs only
+    if (const char *env = getenv("RVDD_FUSE_FIRST")) c->fuse_first = atoi(env);
     CK(cudaStreamCreateWithFlags(&c->st_compute, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking));
@@ -365,11 +368,11 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
     CK(c->pyr.ensure(sizeof(float) * (size_t)(2 * K) * P.total));
     CK(c->tmp.ensure(sizeof(float) * (size_t)(2 * K) * plane));
     CK(c->scratch.ensure(sizeof(float) * (size_t)G * scratch_stride));
-    // small: [slots 2K ints][status 32 ints][bar G*32 uints][partials G*2*C doubles]
+    // small: [slots 2K ints][status 32 ints][bar G*32 uints][partials G*4*C doubles]
     const size_t off_status = ((size_t)2 * K * sizeof(int) + 255) & ~(size_t)255;
     const size_t off_bar = off_status + 256;
     const size_t off_part = (off_bar + (size_t)G * 32 * sizeof(unsigned) + 255) & ~(size_t)255;
-    CK(c->small.ensure(off_part + sizeof(double) * (size_t)G * 2 * C));
+    CK(c->small.ensure(off_part + sizeof(double) * (size_t)G * 4 * C));
     CK(c->table.ensure(sizeof(void *) * (size_t)2 * K));
     char *small = (char *)c->small.p;
     int *slots = (int *)small;
@@ -451,6 +454,8 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
     A.bar = bar; A.partials = partials; A.status = status;
     A.ngroups = G; A.ctas_per_group = C;
     A.spin_limit = c->spin_limit;
+    A.fuse_min_px = c->fuse_min_px;
+    A.fuse_first = c->fuse_first;
     if (iters) CK(cudaMemsetAsync(iters, 0, sizeof(int) * (size_t)K * RVDD_TRACE_SCALES * p.nwarps, st));
     if (c->prof) {
         if ((int)c->prof_ev.size() < 2 * (c->prof_n + 1)) {

@@ -42,11 +42,13 @@ struct SolverArgs {
     int *iters_out;                     // [npairs][RVDD_MAX_SCALES][nwarps] or null
     float *err_out;                     // same shape, error at loop exit, or null
     unsigned *bar;                      // [ngroups * 32] (one counter per 128 B)
-    double *partials;                   // [ngroups][2][ctas_per_group]
+    double *partials;                   // [ngroups][2 slots][2 sums][ctas_per_group]
     unsigned long long *scale_ns;       // optional [npairs][RVDD_MAX_SCALES + 1] globaltimer stamps (profiling)
     int *status;                        // [0]: watchdog flag
     int ngroups, ctas_per_group;
     long long spin_limit;               // watchdog, in clock64 ticks
+    int fuse_min_px;                    // levels with at least this many pixels (and nx % 4 == 0) run two iterations per pass
+    int fuse_first;                     // ... after this many single iterations of every inner loop
 };
 
 // prep.cu

@@ -47,7 +47,7 @@ struct GroupCtx {
     unsigned *bar;          // this group's counter
     unsigned target;        // value the counter reaches when everybody has arrived (thread 0 only)
     int nctas, cta;         // group size, rank inside the group
-    double *partials;       // [2][nctas]
+    double *partials;       // [2 slots][2 sums][nctas]
     int *status;
     long long spin_limit;
     int slot;
@@ -121,8 +121,16 @@ __device__ __forceinline__ double group_sum(const GroupCtx &g, int slot, double 
 #define ST_OFF_U 416
 #define ST_OFF_P 704
 #define ST_ROW 1248                      // floats per stage (4992 B, a multiple of 128 B)
+// RVDD_FUSE2 compiles the two-iterations-per-pass path in (iterate2_strip_tma below).  It is OFF in the shipped library:
+// measured on B200 (29 pairs 1280x720, profiles/solver_fused2_r02.txt) the fused pass halves the DRAM traffic (112 vs 191
+// GB) but the kernel is bound by dependent-issue latency at 12 warps per SM, not by HBM -- 48.6 ms against 42.1 ms --
+// and merely compiling both loops into one kernel costs the single-iteration loop 15 % (register allocation).
 #ifndef ST_STAGES
+#ifdef RVDD_FUSE2
+#define ST_STAGES 3                      // the fused pass keeps rows L-1 and L while row L+1 is in flight
+#else
 #define ST_STAGES 2
+#endif
 #endif
 #define ST_WARP_BYTES (ST_STAGES * ST_ROW * 4 + 128)  // + the mbarriers; keeps every warp's stages 128-byte aligned
 
@@ -300,6 +308,283 @@ __device__ __forceinline__ double iterate_strip_tma(const SolverArgs &SA, int gr
     return err;
 }
 
+// ------------------------------------------------------------------------------------------------ two fused iterations
+//
+// One pass over the strip performs TWO primal-dual iterations (A, then B) and moves the state through HBM once: 60 B per
+// pixel for two iterations instead of 120.  A warp covers 128 columns [c0, c0 + 128) but only lanes 1..30 (120 columns)
+// own output pixels; lanes 0 and 31 recompute the halo columns that the second iteration's stencils reach into, so the
+// horizontal neighbours travel by warp shuffle (no redundant fifth column, no lane-31 special case).  Vertically the strip
+// is a software pipeline over the staged rows: with row L newly staged,
+//   S1  primal A of row L      u^A(L)   from u^k(L), consts(L), p^k(L), p^k(L-1)            (rows L-1, L still in the ring)
+//   S2  dual   A of row L-1    p^A(L-1) from p^k(L-1), u^A(L-1), u^A(L)
+//   S3  primal B of row L-1    u^B(L-1) from u^A(L-1), consts(L-1), p^A(L-1), p^A(L-2)
+//   S4  dual   B of row L-2    p^B(L-2) from p^A(L-2), u^B(L-2), u^B(L-1)   -> store u^B(L-2), p^B(L-2)
+// so a lane carries u^A(L), p^A(L-1) and u^B(L-1) (32 floats) from one row to the next.  A strip of rows [y0, y1) stages
+// rows y0-2 .. y1+1 (three halo rows of iteration A, one of iteration B).  Both iterations' residual sums are produced
+// (own pixels only), so the reference's stopping rule is still evaluated after EVERY iteration: if iteration A already
+// met it, the caller replays ONE single iteration from the untouched input buffers (solver_kernel).  Same arithmetic,
+// operation for operation, as the single-iteration path; only the data path differs.
+
+#define F2_OUT 120                       // columns owned by one warp (lanes 1..30)
+
+struct F2Edges {
+    bool left, last_own, edge_seg;       // lane's first pixel is column 0 / last pixel is column nx-1 / warp touches a border
+};
+
+__device__ __forceinline__ void ld4s(const float *s, float (&d)[4])
+{
+    const float4 t = *reinterpret_cast<const float4 *>(s);
+    d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
+}
+
+// thresholding + primal update of 4 pixels of one row (eval_div + eval_primal of solver_core.h without the fifth column):
+// u = flow before this iteration, (gx, gy, rc) = per-warp constants, (a11, a21, b12, b22) = dual variable of the row,
+// (l11, l21) = its left neighbours (0 on the first column), (up12, up22) = p12 / p22 of the row above (0 on the first row).
+__device__ __forceinline__ void f2_primal(const float (&u1)[4], const float (&u2)[4], const float (&gx)[4], const float (&gy)[4],
+                                          const float (&rc)[4], const float (&a11)[4], const float (&a21)[4],
+                                          const float (&b12)[4], const float (&b22)[4], float l11, float l21,
+                                          const float (&up12)[4], const float (&up22)[4], bool first, bool last,
+                                          const F2Edges &E, const IterConsts &K, float (&n1)[4], float (&n2)[4], float (&res)[4])
+{
+#if defined(__CUDA_ARCH__)      // the straight-line exact operations only exist in the device pass
+    float d1[4], d2[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const bool lastcol = (j == 3) && E.last_own;
+        const float a1 = lastcol ? 0.f : a11[j], a2 = lastcol ? 0.f : a21[j];
+        const float c1 = last ? 0.f : b12[j], c2 = last ? 0.f : b22[j];
+        d1[j] = rvdd_div_inner(a1, j ? a11[j ? j - 1 : 0] : l11, c1, up12[j]);
+        d2[j] = rvdd_div_inner(a2, j ? a21[j ? j - 1 : 0] : l21, c2, up22[j]);
+    }
+    if (E.edge_seg && !first && !last) {         // first / last column of a middle row: (s + b) - bu (mask.c:80-81)
+        if (E.left) {
+            d1[0] = rvdd_div_edge(a11[0], b12[0], up12[0]);
+            d2[0] = rvdd_div_edge(a21[0], b22[0], up22[0]);
+        }
+        if (E.last_own) {
+            d1[3] = rvdd_div_edge(-a11[2], b12[3], up12[3]);
+            d2[3] = rvdd_div_edge(-a21[2], b22[3], up22[3]);
+        }
+    }
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        rvdd_primal_px_fast(u1[j], u2[j], gx[j], gy[j], rvdd_grad2(gx[j], gy[j]), rc[j], d1[j], d2[j], K.l_t, K.theta, K.g0f, &n1[j],
+                            &n2[j], bad);
+    if (bad) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float2 n = rvdd_primal_px_slow(u1[j], u2[j], gx[j], gy[j], rvdd_grad2(gx[j], gy[j]), rc[j], d1[j], d2[j], K.l_t,
+                                                 K.theta, K.g0f);
+            n1[j] = n.x;
+            n2[j] = n.y;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) res[j] = rvdd_residual_px(n1[j], u1[j], n2[j], u2[j]);
+#endif
+}
+
+// dual update of 4 pixels of one row (finish_row of solver_core.h): n = NEW flow of the row, (r1, r2) = its right neighbour
+// (lane + 1), (m1, m2) = NEW flow of the row below; p in: old dual variable, out: new.
+__device__ __forceinline__ void f2_dual(const float (&n1)[4], const float (&n2)[4], float r1, float r2, const float (&m1)[4],
+                                        const float (&m2)[4], bool down, const F2Edges &E, const IterConsts &K, float (&p11)[4],
+                                        float (&p12)[4], float (&p21)[4], float (&p22)[4])
+{
+#if defined(__CUDA_ARCH__)
+    float u1x[4], u2x[4], u1y[4], u2y[4], o11[4], o12[4], o21[4], o22[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const bool lastcol = (j == 3) && E.last_own;
+        u1x[j] = lastcol ? 0.f : FSUB(j < 3 ? n1[j < 3 ? j + 1 : 3] : r1, n1[j]);
+        u2x[j] = lastcol ? 0.f : FSUB(j < 3 ? n2[j < 3 ? j + 1 : 3] : r2, n2[j]);
+        u1y[j] = down ? FSUB(m1[j], n1[j]) : 0.f;
+        u2y[j] = down ? FSUB(m2[j], n2[j]) : 0.f;
+        o11[j] = p11[j]; o12[j] = p12[j]; o21[j] = p21[j]; o22[j] = p22[j];
+    }
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        rvdd_dual_px_fast(&o11[j], &o12[j], u1x[j], u1y[j], K.taut, bad);
+        rvdd_dual_px_fast(&o21[j], &o22[j], u2x[j], u2y[j], K.taut, bad);
+    }
+    if (bad) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float2 a = rvdd_dual_px_slow(p11[j], p12[j], u1x[j], u1y[j], K.taut);
+            const float2 b = rvdd_dual_px_slow(p21[j], p22[j], u2x[j], u2y[j], K.taut);
+            o11[j] = a.x; o12[j] = a.y; o21[j] = b.x; o22[j] = b.y;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) { p11[j] = o11[j]; p12[j] = o12[j]; p21[j] = o21[j]; p22[j] = o22[j]; }
+#endif
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity, int *status)
+{
+    bool ok = mbar_try_wait(bar, parity);
+    for (unsigned spins = 0; !ok; ++spins) {
+        ok = mbar_try_wait(bar, parity);
+        if (!ok && spins > (1u << 22)) {            // ~ seconds: something is badly wrong, do not hang the GPU
+            atomicExch(status, 2);
+            break;
+        }
+    }
+}
+
+// One warp's strip of the fused pass: columns [c0, c0 + 128) (lanes 1..30 own c0 + 4 .. c0 + 123), output rows [y0, y1).
+__device__ __forceinline__ void iterate2_strip_tma(const SolverArgs &SA, int group, const IterPtrs &P, TmaRing &T, int lane, int c0,
+                                                   int y0, int y1, int nx, int ny, const IterConsts &K, int *status, double &errA,
+                                                   double &errB)
+{
+    const int x0 = c0 + 4 * lane;
+    const bool in_img = (x0 >= 0) && (x0 < nx);
+    const bool owner = in_img && lane >= 1 && lane <= 30;
+    F2Edges E;
+    E.left = (x0 == 0);
+    E.last_own = (x0 + 4 == nx);
+    E.edge_seg = (c0 <= 0) || (c0 + 128 >= nx);
+    const int R0 = max(y0 - 2, 0), R1 = min(y1 + 1, ny - 1), Lstart = max(y0 - 1, 0);
+    const int nrows = R1 - R0 + 1;
+    TmaSrc Q;
+    Q.c0 = R0 * nx + c0 - ST_PAD;
+    Q.row_c = group * RVDD_NPLANES + RVDD_PL_C; Q.row_u = group * RVDD_NPLANES + RVDD_PL_U + 2 * P.uc;
+    Q.row_p = group * RVDD_NPLANES + RVDD_PL_P + 4 * P.pc;
+
+    __syncwarp();
+    const unsigned n0 = T.issued;                        // the ring is empty between strips
+    if (elect_one()) {
+        fence_proxy_async();                             // other CTAs' stores (generic proxy) -> our bulk reads
+#pragma unroll
+        for (int k = 0; k < ST_STAGES; k++)
+            if (k < nrows) tma_issue_row(SA, Q, k * nx, T, n0 + k);
+    }
+    T.issued = n0 + (unsigned)min(nrows, ST_STAGES);
+
+    // carried between rows: u^A of the last staged row, p^A and u^B of the row before it
+    float uA1[4], uA2[4], pA11[4], pA12[4], pA21[4], pA22[4], uB1[4], uB2[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) uA1[j] = uA2[j] = pA11[j] = pA12[j] = pA21[j] = pA22[j] = uB1[j] = uB2[j] = 0.f;
+    const long long colq = x0;                           // float offset of the lane's pixels inside a row
+
+#pragma unroll 1
+    for (int L = R0; L <= y1 + 1; ++L) {
+        const bool haveL = (L <= R1);
+        const unsigned iL = n0 + (unsigned)(L - R0);
+        const float *sL = T.stage(iL % ST_STAGES) + ST_PAD + 4 * lane;                       // row L
+        const float *sM = T.stage((iL + ST_STAGES - 1) % ST_STAGES) + ST_PAD + 4 * lane;     // row L - 1
+        if (haveL) mbar_wait(T.bar(iL % ST_STAGES), (iL / ST_STAGES) & 1u, status);
+
+        // ---- S1: primal A of row L
+        float nA1[4], nA2[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) nA1[j] = nA2[j] = 0.f;
+        if (haveL && L >= Lstart) {
+            float u1[4], u2[4], gx[4], gy[4], rc[4], a11[4], a21[4], b12[4], b22[4], up12[4], up22[4], res[4];
+            ld4s(sL + ST_OFF_P, a11); ld4s(sL + ST_OFF_P + 2 * ST_SLOT, a21);
+            ld4s(sL + ST_OFF_P + ST_SLOT, b12); ld4s(sL + ST_OFF_P + 3 * ST_SLOT, b22);
+            const float l11 = E.left ? 0.f : sL[ST_OFF_P - 1], l21 = E.left ? 0.f : sL[ST_OFF_P + 2 * ST_SLOT - 1];
+            if (L > 0) {
+                ld4s(sM + ST_OFF_P + ST_SLOT, up12); ld4s(sM + ST_OFF_P + 3 * ST_SLOT, up22);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) up12[j] = up22[j] = 0.f;
+            }
+            ld4s(sL + ST_OFF_U, u1); ld4s(sL + ST_OFF_U + ST_SLOT, u2);
+            ld4s(sL + ST_OFF_C, gx); ld4s(sL + ST_OFF_C + ST_SLOT, gy); ld4s(sL + ST_OFF_C + 2 * ST_SLOT, rc);
+            f2_primal(u1, u2, gx, gy, rc, a11, a21, b12, b22, l11, l21, up12, up22, L == 0, L == ny - 1, E, K, nA1, nA2, res);
+            if (owner && L >= y0 && L < y1) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) errA += (double)res[j];
+            }
+        }
+
+        // ---- S2: dual A of row L - 1 (its forward differences need u^A of rows L - 1 and L)
+        const int r = L - 1;
+        const bool s2 = (r >= Lstart) && (r <= ny - 1);
+        float qA11[4], qA12[4], qA21[4], qA22[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) qA11[j] = qA12[j] = qA21[j] = qA22[j] = 0.f;
+        if (s2) {
+            ld4s(sM + ST_OFF_P, qA11); ld4s(sM + ST_OFF_P + ST_SLOT, qA12);
+            ld4s(sM + ST_OFF_P + 2 * ST_SLOT, qA21); ld4s(sM + ST_OFF_P + 3 * ST_SLOT, qA22);
+            const float r1 = __shfl_down_sync(0xffffffffu, uA1[0], 1), r2 = __shfl_down_sync(0xffffffffu, uA2[0], 1);
+            f2_dual(uA1, uA2, r1, r2, nA1, nA2, haveL, E, K, qA11, qA12, qA21, qA22);
+        }
+
+        // ---- S3: primal B of row L - 1
+        const bool s3 = s2 && (r >= y0);
+        float nB1[4], nB2[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) nB1[j] = nB2[j] = 0.f;
+        if (s3) {
+            float gx[4], gy[4], rc[4], up12[4], up22[4], res[4];
+            ld4s(sM + ST_OFF_C, gx); ld4s(sM + ST_OFF_C + ST_SLOT, gy); ld4s(sM + ST_OFF_C + 2 * ST_SLOT, rc);
+            const float t11 = __shfl_up_sync(0xffffffffu, qA11[3], 1), t21 = __shfl_up_sync(0xffffffffu, qA21[3], 1);
+            const float l11 = E.left ? 0.f : t11, l21 = E.left ? 0.f : t21;
+#pragma unroll
+            for (int j = 0; j < 4; j++) { up12[j] = r > 0 ? pA12[j] : 0.f; up22[j] = r > 0 ? pA22[j] : 0.f; }
+            f2_primal(uA1, uA2, gx, gy, rc, qA11, qA21, qA12, qA22, l11, l21, up12, up22, r == 0, r == ny - 1, E, K, nB1, nB2, res);
+            if (owner && r < y1) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) errB += (double)res[j];
+            }
+        }
+
+        // ---- S4: dual B of row L - 2, stores
+        const int q = L - 2;
+        if (q >= y0 && q < y1) {
+            const float r1 = __shfl_down_sync(0xffffffffu, uB1[0], 1), r2 = __shfl_down_sync(0xffffffffu, uB2[0], 1);
+            f2_dual(uB1, uB2, r1, r2, nB1, nB2, q + 1 <= ny - 1, E, K, pA11, pA12, pA21, pA22);
+            if (owner) {
+                const long long o = (long long)q * nx + colq;
+                Vec<4>::st(P.nu1() + o, uB1);
+                Vec<4>::st(P.nu2() + o, uB2);
+                Vec<4>::st(P.np11() + o, pA11);
+                Vec<4>::st(P.np12() + o, pA12);
+                Vec<4>::st(P.np21() + o, pA21);
+                Vec<4>::st(P.np22() + o, pA22);
+            }
+        }
+
+        // ---- rotate the carried rows
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uA1[j] = nA1[j]; uA2[j] = nA2[j];
+            pA11[j] = qA11[j]; pA12[j] = qA12[j]; pA21[j] = qA21[j]; pA22[j] = qA22[j];
+            uB1[j] = nB1[j]; uB2[j] = nB2[j];
+        }
+
+        // ---- the stage of row L - 1 is free now: refill it with row L + 2
+        __syncwarp();
+        if (L - 1 >= R0 && L + 2 <= R1) {
+            if (elect_one()) tma_issue_row(SA, Q, (L + 2 - R0) * nx, T, T.issued);
+            T.issued++;
+        }
+    }
+    T.taken = T.issued;
+}
+
+// strip plan of the fused pass: column segments of F2_OUT pixels, the first one starting one (halo) lane left of column 0
+__device__ __forceinline__ void iterate2_group(const SolverArgs &A, int group, const IterPtrs &P, TmaRing &T, int nx, int ny,
+                                               const IterConsts &K, int gwarp, int nwarps_group, int *status, double &errA,
+                                               double &errB)
+{
+    const int lane = threadIdx.x & 31;
+    const int ncol = (nx + F2_OUT - 1) / F2_OUT;
+    int per_col = nwarps_group / ncol;
+    if (per_col < 1) per_col = 1;
+    int rows = (ny + per_col - 1) / per_col;
+    if (rows < 1) rows = 1;
+    const int nstrips = (ny + rows - 1) / rows, total = ncol * nstrips;
+    for (int w = gwarp; w < total; w += nwarps_group) {
+        const int col = w % ncol, strip = w / ncol;
+        const int y0 = strip * rows, y1 = min(ny, y0 + rows);
+        iterate2_strip_tma(A, group, P, T, lane, col * F2_OUT - 4, y0, y1, nx, ny, K, status, errA, errB);
+    }
+}
+
 // Distribute the image over the group's warps: column segments of 32*V pixels, strips of `rows` rows
 // (iterate_strip, the direct-load version, is in solver_core.h and shared with the host-compiled unit tests).
 template <int V>
@@ -382,8 +667,8 @@ __device__ __forceinline__ void warp_consts_group(const float *I0, const float *
 
 __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel(const __grid_constant__ SolverArgs A)
 {
-    __shared__ double s_red[SOLVER_WARPS];
-    __shared__ double s_val;
+    __shared__ double s_red[SOLVER_WARPS], s_red2[SOLVER_WARPS];
+    __shared__ double s_val, s_val2;
     __shared__ int s_flag;
     extern __shared__ __align__(128) unsigned char s_dyn[];
 
@@ -404,7 +689,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
     g.cta = blockIdx.x - group * A.ctas_per_group;
     g.bar = A.bar + group * 32;
     g.target = 0u;
-    g.partials = A.partials + (size_t)group * 2 * A.ctas_per_group;
+    g.partials = A.partials + (size_t)group * 4 * A.ctas_per_group;
     g.status = A.status;
     g.spin_limit = A.spin_limit;
     g.slot = 0;
@@ -473,28 +758,57 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
                     if (!group_sync(g, &s_flag)) return;
                     const unsigned long long tp1 = stamping ? now_ns() : 0ULL;
 
-                    // ---- inner loop (:161-244), stop test after every iteration
+                    // ---- inner loop (:161-244), stop test after every iteration.  Big levels run the first iteration alone
+                    // (many loops stop right there) and then TWO iterations per pass (iterate2_strip_tma): both residuals
+                    // come back, and if the first of the two already met the stopping rule that iteration is replayed
+                    // alone from the input buffers, which the fused pass leaves untouched.
                     int it = 0;
                     float err = INFINITY;
+#if defined(RVDD_FUSE2)
+                    const bool can_fuse = ((nx & 3) == 0) && n >= A.fuse_min_px;
+#else
+                    const bool can_fuse = false;
+#endif
                     while (err > A.eps2 && it < RVDD_MAX_ITERATIONS) {
-                        it++;
                         IterPtrs P;
                         P.S = S; P.PL = PL; P.uc = uc; P.pc = pc;
-                        double e = ((nx & 3) == 0) ? iterate_group<4>(A, group, P, T, nx, ny, K, gwarp, gwarps, A.status)
-                                                   : iterate_group<1>(A, group, P, T, nx, ny, K, gwarp, gwarps, A.status);
-                        // CTA partial in a fixed order, then the group reduction rides on the barrier
-                        for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-                        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = e;
+                        const bool fused = can_fuse && it >= A.fuse_first && it + 2 <= RVDD_MAX_ITERATIONS;
+                        double e = 0.0, e2 = 0.0;
+#if defined(RVDD_FUSE2)
+                        if (fused)
+                            iterate2_group(A, group, P, T, nx, ny, K, gwarp, gwarps, A.status, e, e2);
+                        else
+#endif
+                            e = ((nx & 3) == 0) ? iterate_group<4>(A, group, P, T, nx, ny, K, gwarp, gwarps, A.status)
+                                                : iterate_group<1>(A, group, P, T, nx, ny, K, gwarp, gwarps, A.status);
+                        // CTA partials in a fixed order, then the group reduction rides on the barrier
+                        for (int o = 16; o > 0; o >>= 1) {
+                            e += __shfl_xor_sync(0xffffffffu, e, o);
+                            if (fused) e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+                        }
+                        if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5] = e; s_red2[threadIdx.x >> 5] = e2; }
                         __syncthreads();
                         if (threadIdx.x == 0) {
-                            double t = 0.0;
-                            for (int k = 0; k < SOLVER_WARPS; k++) t += s_red[k];
-                            g.partials[(size_t)g.slot * g.nctas + g.cta] = t;
+                            double t = 0.0, t2 = 0.0;
+                            for (int k = 0; k < SOLVER_WARPS; k++) { t += s_red[k]; t2 += s_red2[k]; }
+                            g.partials[(size_t)(2 * g.slot) * g.nctas + g.cta] = t;
+                            g.partials[(size_t)(2 * g.slot + 1) * g.nctas + g.cta] = t2;
                         }
                         if (!group_sync(g, &s_flag)) return;
-                        const double tot = group_sum(g, g.slot, &s_val);
+                        const double tot = group_sum(g, 2 * g.slot, &s_val);
+                        const double tot2 = fused ? group_sum(g, 2 * g.slot + 1, &s_val2) : 0.0;
                         g.slot ^= 1;
                         err = FDIV((float)tot, (float)n);        // error /= size (:223)
+                        if (!fused) {
+                            it++;
+                        } else if (err > A.eps2) {               // the loop continues past iteration A: B is the state
+                            it += 2;
+                            err = FDIV((float)tot2, (float)n);
+                        } else {                                 // the reference stops after iteration A: replay it alone
+                            iterate_group<4>(A, group, P, T, nx, ny, K, gwarp, gwarps, A.status);
+                            if (!group_sync(g, &s_flag)) return;
+                            it++;
+                        }
                         uc ^= 1;
                         pc ^= 1;
                     }

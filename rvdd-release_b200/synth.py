@@ -130,3 +130,90 @@ def exact_gray_pair(h, w, seed=7, noise=True):
             raw = raw + np.sqrt(var) * (s / 37837.0)    # sum of 4 uniforms: standard deviation 65536 / sqrt(3) = 37837
         out.append(np.ascontiguousarray(raw.astype(np.float32)))
     return out[0], out[1]
+
+
+# ------------------------------------------------------------------------------------------------ exact sequences
+#
+# Sequences for fixtures that must be regenerated bit for bit on another machine AND on another device (golden vectors of
+# the full-size pipeline configurations are made on the CPU of the build container and replayed on the GPU box): only
+# int64 hashing and IEEE float64 + - * / floor sqrt, each as its own torch op (no fused multiply-add, no libm).
+
+_M64 = (1 << 64) - 1
+
+
+def _wrap(v):
+    """Python int -> the int64 value with the same 64-bit pattern."""
+    v &= _M64
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def _lsr(x, k):
+    """logical right shift of an int64 tensor"""
+    return (x >> k) & ((1 << (64 - k)) - 1)
+
+
+def _hash64(x):
+    """splitmix64 finaliser on an int64 tensor (wrap-around arithmetic)."""
+    x = x + _wrap(0x9E3779B97F4A7C15)
+    x = (x ^ _lsr(x, 30)) * _wrap(0xBF58476D1CE4E5B9)
+    x = (x ^ _lsr(x, 27)) * _wrap(0x94D049BB133111EB)
+    return x ^ _lsr(x, 31)
+
+
+def _tri(v):
+    """triangle wave in [0, 1] with period 2 (exact operations only)"""
+    return torch.abs(v - 2.0 * torch.floor(v / 2.0) - 1.0)
+
+
+def _value_noise(cy, cx, cell, salt):
+    """bilinear interpolation of hashed lattice values in [0, 1023] at float64 coordinates (cy, cx)"""
+    gy, gx = cy / cell, cx / cell
+    iy, ix = torch.floor(gy), torch.floor(gx)
+    fy, fx = gy - iy, gx - ix
+    iy, ix = iy.to(torch.int64), ix.to(torch.int64)
+
+    def lat(dy, dx):
+        key = (iy + dy) * 1000003 + (ix + dx) * 7919 + salt * 104729
+        return (_hash64(key) & 1023).to(torch.float64)
+
+    a, b, c, d = lat(0, 0), lat(0, 1), lat(1, 0), lat(1, 1)
+    top = a + fx * (b - a)
+    bot = c + fx * (d - c)
+    return top + fy * (bot - top)
+
+
+_OCTAVES = ((64.0, 1.0), (16.0, 0.5), (6.0, 0.25))
+
+
+def exact_clean_frame(t, h, w, device="cpu"):
+    """Noise-free frame t at the 4 Bayer sub-pixel phases, (h, w, 4) float64 in [0, 1]."""
+    y, x = torch.meshgrid(torch.arange(h, dtype=torch.float64, device=device),
+                          torch.arange(w, dtype=torch.float64, device=device), indexing="ij")
+    tt = float(t)
+    px = x - 2.5 * tt - 4.0 * _tri(y / 97.0 + 0.35 * tt) + 4096.0
+    py = y + 1.5 * tt - 3.0 * _tri(x / 131.0 + 0.25 * tt) + 4096.0
+    out = []
+    for dx, dy in _PHASES:
+        v = torch.zeros_like(x)
+        for k, (cell, amp) in enumerate(_OCTAVES):
+            v = v + amp * _value_noise(py + dy, px + dx, cell, k)
+        out.append(v / (1023.0 * sum(a for _, a in _OCTAVES)))
+    return torch.stack(out, dim=-1)
+
+
+def exact_sequence(n_frames, h, w, iso="iso3200", device="cpu", noise_seed=0):
+    """``(n_frames, h, w, 4)`` float32 packed-raw-like frames, bit-identical on every machine and device: hashed value-noise
+    texture advected by a smooth ~3 px motion, raw range and heteroscedastic noise model of ``ISO[iso]`` (the noise is a
+    sum of four 16-bit uniforms per sample instead of a Gaussian)."""
+    cfg = ISO[iso]
+    frames = []
+    idx = torch.arange(h * w * 4, dtype=torch.int64, device=device).reshape(h, w, 4)
+    for t in range(n_frames):
+        raw = cfg["lo"] + exact_clean_frame(t, h, w, device) * (cfg["hi"] - cfg["lo"])
+        if cfg["a"] != 0.0:
+            r = _hash64(idx + (noise_seed * 1000 + t) * 1000000007)
+            s = ((r & 65535) + (_lsr(r, 16) & 65535) + (_lsr(r, 32) & 65535) + _lsr(r, 48)).to(torch.float64) - 2.0 * 65535.0
+            var = torch.clamp(cfg["a"] * raw + cfg["b"], min=0.0)
+            raw = raw + torch.sqrt(var) * (s / 37837.0)
+        frames.append(torch.clamp(raw, 0.0, 4095.0).to(torch.float32))
+    return torch.stack(frames, 0)

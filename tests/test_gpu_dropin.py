@@ -173,3 +173,24 @@ def test_watchdog_poisons_the_result(bridge):
         assert bool(torch.isfinite(flow).all())
     finally:
         b.close()
+
+
+def test_fused_two_iteration_variant_is_bit_exact(libpath, port):
+    """The -DRVDD_FUSE2 build (two primal-dual iterations per pass with a speculative exact stop and a one-iteration
+    replay; measured slower than the shipped pass and therefore off by default) must still give the
+    reference's bits and iteration counts."""
+    from rvdd_release_b200 import bridge as B
+    variant = os.path.join(os.path.dirname(libpath), "libBridge_fuse2.so")
+    if not os.path.exists(variant):
+        pytest.skip("variant library not built")
+    b = B.Bridge(variant)
+    try:
+        for h, w, iso in ((180, 320, "iso3200"), (97, 132, "iso12800"), (360, 640, "clean"), (720, 1280, "iso3200")):
+            I0, I1 = synth.gray_pair(h, w, iso)
+            ref, it_ref, _, _, _ = port.tvl1flow_traced(I0, I1, err_mode=0)
+            gray = torch.from_numpy(np.stack([I0, I1])).cuda()
+            flow, iters = b.tvl1_flow(gray, [1], [0], trace=True, check=True)
+            assert np.array_equal(iters[0, :it_ref.shape[0]].cpu().numpy(), it_ref), (h, w)
+            assert np.array_equal(flow[0].cpu().numpy(), ref), (h, w)
+    finally:
+        b.close()

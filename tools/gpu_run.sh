@@ -1,8 +1,9 @@
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "precompute" 2>&1 | tail -3
-df -h /dev/shm /tmp | tail -3; nproc; free -g | head -2
-python profiles/bench_precompute.py --seqs-per-gpu 12 > gpurun_out/c4_1gpu_shm.json 2> gpurun_out/c4_1gpu_shm.err; tail -3 gpurun_out/c4_1gpu_shm.err
-python profiles/bench_precompute.py --seqs-per-gpu 12 --readers 8 --writers 8 > gpurun_out/c4_1gpu_shm_r8w8.json 2>/dev/null
-python profiles/bench_precompute.py --seqs-per-gpu 12 --readers 2 --writers 2 > gpurun_out/c4_1gpu_shm_r2w2.json 2>/dev/null
-python profiles/bench_precompute.py --seqs-per-gpu 6 --root /tmp/rvdd_config4 > gpurun_out/c4_1gpu_disk.json 2>/dev/null
-cat gpurun_out/c4_*.json
+for r in 1 2; do
+for v in s2 s3nf; do
+RVDD_BRIDGE_LIB=rvdd-release_b200/lib/libBridge_$v.so python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/r2d_${v}_$r.json 2>/dev/null
+done
+python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/r2d_fused_$r.json 2>/dev/null
+done
+python tools/prof_solver.py 29 > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:solver_kernel -s 2 -c 1 -o gpurun_out/solver_r02b_fused python tools/prof_solver.py 29 > gpurun_out/ncu.log 2>&1
+echo ncu_rc=$?

@@ -282,6 +282,65 @@ def run_ours(args, rank, local_rank, world):
         e2e_s = float(t.item())
     e2e_value = world * npairs * e2e_steps / e2e_s
 
+    # ---- the same stream with the warped frames left on the device: what the reference's dataset constructor keeps when
+    # gen_warp is off (base_dataset.py:178-189: the warp is computed and thrown away, only the flow is written)
+    def e2e_run_discard(nsteps):
+        for i in range(nsteps):
+            s_ = i & 1
+            br.wait_host(s_)
+            br.submit_host(s_, h_frames[s_], src, tgt, h_flow[s_], None, discard_warp=True)
+        br.wait_host(0)
+        br.wait_host(1)
+
+    e2e_run_discard(2)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_run_discard(e2e_steps)
+    e2e_nw_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_nw_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_nw_s = float(t.item())
+    e2e_nw_value = world * npairs * e2e_steps / e2e_nw_s
+
+    # ---- copy ceiling of this box: the e2e step's host<->device traffic alone (same pinned buffers and sizes, H2D and D2H
+    # on two streams, no kernels), all ranks at once -- what `e2e` could reach if compute were free
+    d_in = torch.empty_like(frames)
+    d_flow = torch.empty((npairs, H, W, 2), dtype=torch.float32, device=dev)
+    d_warp = torch.empty((npairs, H, W, CH), dtype=torch.float32, device=dev)
+    s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def copy_run(nsteps, with_warp):
+        for i in range(nsteps):
+            s_ = i & 1
+            with torch.cuda.stream(s_up):
+                d_in.copy_(h_frames[s_], non_blocking=True)
+            with torch.cuda.stream(s_down):
+                h_flow[s_].copy_(d_flow, non_blocking=True)
+                if with_warp:
+                    h_warp[s_].copy_(d_warp, non_blocking=True)
+        s_up.synchronize()
+        s_down.synchronize()
+
+    ceil = {}
+    for name, ww in (("with_warped_frames", True), ("flows_only", False)):
+        copy_run(2, ww)
+        barrier()
+        t0 = time.perf_counter()
+        copy_run(e2e_steps, ww)
+        dtc = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dtc], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dtc = float(t.item())
+        ceil[name] = world * npairs * e2e_steps / dtc
+    bytes_step = int(h_frames[0].numel() * 4 + h_flow[0].numel() * 4 + h_warp[0].numel() * 4)
+    copy_ceiling = {"pairs_per_s_with_warped_frames": ceil["with_warped_frames"], "pairs_per_s_flows_only": ceil["flows_only"],
+                    "aggregate_GBps_with_warped_frames": ceil["with_warped_frames"] / npairs * bytes_step / 1e9,
+                    "what": "H2D of the step's frames + D2H of its results through pinned memory, two streams, no kernels, "
+                            "all ranks concurrently"}
+    del d_in, d_flow, d_warp
+
     # ---- the literal drop-in: the one symbol the reference binds (library.py:145-148), host numpy buffers, one pair per
     # call, flow only (what a plain copy of build/libBridge.so into the reference delivers without any other change)
     dropin = None
@@ -346,7 +405,11 @@ def run_ours(args, rank, local_rank, world):
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h_frames.numel() * 4),
                 "d2h_bytes_per_step": int((h_flow.numel() + h_warp.numel()) * 4), "steps": e2e_steps,
                 "api": "rvdd_flow_and_warp_host_submit/_wait, 2 slots in flight (pinned host buffers)",
-                "single_blocking_call_value": npairs / e2e_sync_s},
+                "single_blocking_call_value": npairs / e2e_sync_s,
+                "gen_warp_false": {"value": e2e_nw_value, "unit": "pairs/s", "d2h_bytes_per_step": int(h_flow.numel() * 4),
+                                   "what": "warp computed on the device and discarded, only flows downloaded "
+                                           "(base_dataset.py:178-189 with gen_warp off)"},
+                "copy_ceiling": copy_ceiling},
         "dropin_single_call": dropin,
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roofline,

@@ -179,6 +179,22 @@ RVDD_API int rvdd_flow_and_warp_host_submit(rvdd_ctx *ctx, int slot, const float
                                             int *iters_host);
 RVDD_API int rvdd_flow_and_warp_host_wait(rvdd_ctx *ctx, int slot);
 
+/* The same submission with an explicit policy for the warped frames, following the reference's dataset constructor
+ * (data/base_dataset.py:178-189): `compute_flow_and_warp` always warps the source frame, but the result is only kept
+ * (written to <wFolder>) when gen_warp is set.
+ *   RVDD_WARP_SKIP     no warp at all (warped_host ignored);
+ *   RVDD_WARP_DOWNLOAD warp on the device and copy it to warped_host (what rvdd_flow_and_warp_host_submit does when
+ *                      warped_host is not NULL);
+ *   RVDD_WARP_DISCARD  warp on the device, leave it there (gen_warp = False: the work of the reference's call, without
+ *                      moving frames nobody reads). */
+#define RVDD_WARP_SKIP 0
+#define RVDD_WARP_DOWNLOAD 1
+#define RVDD_WARP_DISCARD 2
+RVDD_API int rvdd_flow_and_warp_host_submit_ex(rvdd_ctx *ctx, int slot, const float *frames_host, int nframes, int h, int w,
+                                               int c, const int *src, const int *tgt, int npairs,
+                                               const rvdd_tvl1_params *params, float *flow_host, float *warped_host,
+                                               int *iters_host, int warp_mode);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,9 @@ _SIGNATURES = {
                                                  C.c_void_p, C.c_void_p, C.c_int, C.POINTER(TVL1Params), C.c_void_p,
                                                  C.c_void_p, C.c_void_p]),
     "rvdd_flow_and_warp_host_wait": (C.c_int, [C.c_void_p, C.c_int]),
+    "rvdd_flow_and_warp_host_submit_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                    C.c_void_p, C.c_void_p, C.c_int, C.POINTER(TVL1Params), C.c_void_p,
+                                                    C.c_void_p, C.c_void_p, C.c_int]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -288,17 +291,19 @@ class Bridge:
         return flow, warped, iters
 
 
-    def submit_host(self, slot, frames, src, tgt, flow_out, warped_out=None, params=None):
-        """Asynchronous half of flow_and_warp_host on staging slot 0 / 1 (rvdd_flow_and_warp_host_submit).  `frames`,
+    def submit_host(self, slot, frames, src, tgt, flow_out, warped_out=None, params=None, discard_warp=False):
+        """Asynchronous half of flow_and_warp_host on staging slot 0 / 1 (rvdd_flow_and_warp_host_submit_ex).  `frames`,
         `flow_out`, `warped_out` are CPU float32 tensors (pin them to let the copies overlap) that must stay alive and
-        untouched until wait_host(slot)."""
+        untouched until wait_host(slot).  discard_warp=True (with warped_out=None) warps on the device without downloading
+        the result -- the reference's gen_warp=False case (base_dataset.py:178-189)."""
         n, h, w, c = frames.shape
         src = np.ascontiguousarray(src, dtype=np.int32)
         tgt = np.ascontiguousarray(tgt, dtype=np.int32)
-        self._ck(self.lib.rvdd_flow_and_warp_host_submit(
+        mode = 1 if warped_out is not None else (2 if discard_warp else 0)
+        self._ck(self.lib.rvdd_flow_and_warp_host_submit_ex(
             self.ctx, int(slot), frames.data_ptr(), n, h, w, c, src.ctypes.data, tgt.ctypes.data, int(src.size),
             C.byref(params) if params else None, flow_out.data_ptr(),
-            warped_out.data_ptr() if warped_out is not None else None, None))
+            warped_out.data_ptr() if warped_out is not None else None, None, mode))
 
     def wait_host(self, slot):
         self._ck(self.lib.rvdd_flow_and_warp_host_wait(self.ctx, int(slot)))

@@ -653,10 +653,26 @@ __global__ void interleave_kernel(const float *__restrict__ planar, float2 *__re
 // with events.  While slot s computes, the other slot can already upload its frames and the previous submission of
 // slot s^1 can still be downloading -- for a stream of sequences (the offline precompute) the copies disappear behind
 // the solver.  A slot must be waited for before it is submitted again.
+extern "C" int rvdd_flow_and_warp_host_submit_ex(rvdd_ctx *c, int slot, const float *frames, int nframes, int h, int w, int ch,
+                                                 const int *src, const int *tgt, int npairs, const rvdd_tvl1_params *params,
+                                                 float *flow_host, float *warped_host, int *iters_host, int warp_mode);
+
 extern "C" int rvdd_flow_and_warp_host_submit(rvdd_ctx *c, int slot, const float *frames, int nframes, int h, int w, int ch,
                                               const int *src, const int *tgt, int npairs, const rvdd_tvl1_params *params,
                                               float *flow_host, float *warped_host, int *iters_host)
 {
+    return rvdd_flow_and_warp_host_submit_ex(c, slot, frames, nframes, h, w, ch, src, tgt, npairs, params, flow_host, warped_host,
+                                             iters_host, warped_host ? RVDD_WARP_DOWNLOAD : RVDD_WARP_SKIP);
+}
+
+extern "C" int rvdd_flow_and_warp_host_submit_ex(rvdd_ctx *c, int slot, const float *frames, int nframes, int h, int w, int ch,
+                                                 const int *src, const int *tgt, int npairs, const rvdd_tvl1_params *params,
+                                                 float *flow_host, float *warped_host, int *iters_host, int warp_mode)
+{
+    if (warp_mode != RVDD_WARP_SKIP && warp_mode != RVDD_WARP_DOWNLOAD && warp_mode != RVDD_WARP_DISCARD)
+        return fail("rvdd_flow_and_warp_host_submit_ex: bad warp_mode");
+    if (warp_mode == RVDD_WARP_DOWNLOAD && !warped_host) return fail("rvdd_flow_and_warp_host_submit_ex: warped_host is null");
+    const bool do_warp = warp_mode != RVDD_WARP_SKIP, get_warp = warp_mode == RVDD_WARP_DOWNLOAD;
     if (!c) return fail("rvdd_flow_and_warp_host_submit: null context");
     if (slot != 0 && slot != 1) return fail("rvdd_flow_and_warp_host_submit: slot must be 0 or 1");
     if (c->slot_busy[slot]) return fail("rvdd_flow_and_warp_host_submit: slot still in flight (call ..._wait first)");
@@ -672,7 +688,7 @@ extern "C" int rvdd_flow_and_warp_host_submit(rvdd_ctx *c, int slot, const float
     CK(b_gray.ensure(sizeof(float) * (size_t)nframes * n));
     CK(b_flow.ensure(sizeof(float) * (size_t)npairs * 2 * n));
     CK(b_hw2.ensure(sizeof(float) * (size_t)npairs * 2 * n));
-    if (warped_host) CK(b_warp.ensure(sizeof(float) * (size_t)npairs * n * ch));
+    if (do_warp) CK(b_warp.ensure(sizeof(float) * (size_t)npairs * n * ch));
     if (iters_host) CK(b_iters.ensure(sizeof(int) * (size_t)npairs * RVDD_TRACE_SCALES * p.nwarps));
     float *d_frames = (float *)b_frames.p, *d_gray = (float *)b_gray.p, *d_flow = (float *)b_flow.p;
     float *d_hw2 = (float *)b_hw2.p, *d_warp = (float *)b_warp.p;
@@ -693,7 +709,7 @@ extern "C" int rvdd_flow_and_warp_host_submit(rvdd_ctx *c, int slot, const float
         interleave_kernel<<<dim3(bx, npairs), 256, 0, st>>>(d_flow, (float2 *)d_hw2, n);
         CK(cudaGetLastError());
     }
-    if (warped_host) {
+    if (do_warp) {
         // single_warp(img1 = source frame, flow) in the frames' own HWC layout (flow_utils.py:105-122, :154); runs of
         // consecutive source frames (a video: sources t-1 = 0, 1, 2, ...) go out as one batched launch
         for (int k = 0; k < npairs;) {
@@ -716,7 +732,7 @@ extern "C" int rvdd_flow_and_warp_host_submit(rvdd_ctx *c, int slot, const float
     // stage 3: download
     CK(cudaStreamWaitEvent(c->st_out, c->slot_compute[slot], 0));
     CK(cudaMemcpyAsync(flow_host, d_hw2, sizeof(float) * (size_t)npairs * 2 * n, cudaMemcpyDeviceToHost, c->st_out));
-    if (warped_host)
+    if (get_warp)
         CK(cudaMemcpyAsync(warped_host, d_warp, sizeof(float) * (size_t)npairs * n * ch, cudaMemcpyDeviceToHost, c->st_out));
     if (iters_host)
         CK(cudaMemcpyAsync(iters_host, d_iters, sizeof(int) * (size_t)npairs * RVDD_TRACE_SCALES * p.nwarps,

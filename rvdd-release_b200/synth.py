@@ -160,14 +160,21 @@ def _hash64(x):
     return x ^ _lsr(x, 31)
 
 
+def _div(a, c):
+    """a / c as a true IEEE division on every device.  (On CUDA, torch turns tensor / python-scalar into a multiplication
+    by the reciprocal, which is not the same number; dividing by a 0-dim tensor ON THE SAME DEVICE takes the ordinary
+    element-wise division kernel.)"""
+    return a / torch.tensor(c, dtype=a.dtype, device=a.device)
+
+
 def _tri(v):
-    """triangle wave in [0, 1] with period 2 (exact operations only)"""
+    """triangle wave in [0, 1] with period 2 (exact operations only; v / 2 is exact either way)"""
     return torch.abs(v - 2.0 * torch.floor(v / 2.0) - 1.0)
 
 
 def _value_noise(cy, cx, cell, salt):
     """bilinear interpolation of hashed lattice values in [0, 1023] at float64 coordinates (cy, cx)"""
-    gy, gx = cy / cell, cx / cell
+    gy, gx = _div(cy, cell), _div(cx, cell)
     iy, ix = torch.floor(gy), torch.floor(gx)
     fy, fx = gy - iy, gx - ix
     iy, ix = iy.to(torch.int64), ix.to(torch.int64)
@@ -190,14 +197,14 @@ def exact_clean_frame(t, h, w, device="cpu"):
     y, x = torch.meshgrid(torch.arange(h, dtype=torch.float64, device=device),
                           torch.arange(w, dtype=torch.float64, device=device), indexing="ij")
     tt = float(t)
-    px = x - 2.5 * tt - 4.0 * _tri(y / 97.0 + 0.35 * tt) + 4096.0
-    py = y + 1.5 * tt - 3.0 * _tri(x / 131.0 + 0.25 * tt) + 4096.0
+    px = x - 2.5 * tt - 4.0 * _tri(_div(y, 97.0) + 0.35 * tt) + 4096.0
+    py = y + 1.5 * tt - 3.0 * _tri(_div(x, 131.0) + 0.25 * tt) + 4096.0
     out = []
     for dx, dy in _PHASES:
         v = torch.zeros_like(x)
         for k, (cell, amp) in enumerate(_OCTAVES):
             v = v + amp * _value_noise(py + dy, px + dx, cell, k)
-        out.append(v / (1023.0 * sum(a for _, a in _OCTAVES)))
+        out.append(_div(v, 1023.0 * sum(a for _, a in _OCTAVES)))
     return torch.stack(out, dim=-1)
 
 
@@ -214,6 +221,6 @@ def exact_sequence(n_frames, h, w, iso="iso3200", device="cpu", noise_seed=0):
             r = _hash64(idx + (noise_seed * 1000 + t) * 1000000007)
             s = ((r & 65535) + (_lsr(r, 16) & 65535) + (_lsr(r, 32) & 65535) + _lsr(r, 48)).to(torch.float64) - 2.0 * 65535.0
             var = torch.clamp(cfg["a"] * raw + cfg["b"], min=0.0)
-            raw = raw + torch.sqrt(var) * (s / 37837.0)
+            raw = raw + torch.sqrt(var) * _div(s, 37837.0)
         frames.append(torch.clamp(raw, 0.0, 4095.0).to(torch.float32))
     return torch.stack(frames, 0)

@@ -73,7 +73,7 @@ def test_checkpoint_psnr_at_configured_geometry(bridge, name):
     al = FrameAligner(depth=1, future_depth=1 if feat_future else 0, feature_channels=48 if feat_future else 0)
     psnrs, means, den = [], [], None
     with torch.no_grad():
-        n = ha((2.0 * (frames / 4095.0) - 1.0).permute(0, 3, 1, 2).contiguous())          # [nfr, 3, 2h, 2w], one launch
+        n = ha((2.0 * synth._div(frames, 4095.0) - 1.0).permute(0, 3, 1, 2).contiguous())   # [nfr, 3, 2h, 2w], one launch
         al.reset(n[0:1])
         for t in range(1, T + 1):
             if feat_future:
@@ -95,3 +95,37 @@ def test_checkpoint_psnr_at_configured_geometry(bridge, name):
     assert np.max(np.abs(np.array(means) - d["denoised_mean"])) <= 1e-3
     last = den[0, :, ::8, ::8].cpu().numpy()
     assert float(np.abs(last - d["denoised_last_sub"]).max()) <= 2e-2      # recurrence-amplified cuDNN-vs-CPU rounding; PSNR is the gate
+
+
+def test_batched_multi_sequence_driver_matches_fixture(bridge):
+    """Config 5's driver shape at a small size: S sequences advance in lock step as the batch dimension of flow -> warp ->
+    denoiser (rvdd_release_b200.infer.run_sequences).  Sequence 0 is the cn_small fixture's, so its PSNRs must match the
+    reference pipeline's; sequence 1 has another noise realisation and must come out the same whether it runs alone or in
+    the batch."""
+    from rvdd_release_b200 import infer
+    from rvdd_release_b200.hamilton_adam import HamiltonAdam
+    d = np.load(os.path.join(GOLDEN, "config_cn_small.npz"))
+    nfr, h, w = (int(v) for v in d["geometry"])
+    iso = str(d["iso"])
+    net = torch.jit.load(os.path.join(GOLDEN, TRACES["cn_small"]), map_location="cuda").eval()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    frames = torch.stack([synth.exact_sequence(nfr, h, w, iso, device="cuda", noise_seed=s) for s in (0, 1, 2)])
+    cfg, ha = synth.ISO[iso], HamiltonAdam("gbrg")
+
+    def gt(t):
+        clean = (cfg["lo"] + synth.exact_clean_frame(t, h, w, device="cuda") * (cfg["hi"] - cfg["lo"])).float()
+        return (2.0 * ha.pack_in_one(clean.permute(2, 0, 1)[None]) / 4095.0 - 1.0)[:, None].repeat(1, 3, 1, 1)
+
+    with torch.no_grad():
+        outs, tm = infer.run_sequences(frames, net, future_depth=1, feature_channels=48, denoiser_batch=2)
+        solo, _ = infer.run_sequences(frames[1:2], net, future_depth=1, feature_channels=48)
+    assert len(outs) == nfr - 2 and tm["pairs"] == 3 * 2 * (nfr - 2) and tm["frames"] == 3 * (nfr - 2)
+    ps = np.array([[float(infer.psnr(o[s:s + 1], gt(t + 1))) for t, o in enumerate(outs)] for s in range(3)])
+    assert np.max(np.abs(ps[0] - d["psnr"])) <= 0.02, (ps[0].tolist(), d["psnr"].tolist())
+    for t in range(nfr - 2):
+        assert float((outs[t][1:2] - solo[t]).abs().max()) <= 1e-4, t          # batch composition does not matter
+    past, fut = infer.compute_all_flows(frames, 1)
+    assert past.shape == (3, nfr - 2, 2, h, w) and fut.shape == (3, nfr - 2, 1, 2, h, w)
+    hw2 = past[0].permute(0, 2, 3, 1).contiguous().cpu().numpy()
+    assert all(_sha(hw2[k]) == str(d["flow_sha"][k]) for k in range(nfr - 2))

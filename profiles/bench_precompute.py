@@ -154,6 +154,34 @@ def main():
     noio_s = max_over_ranks(time.perf_counter() - t0)
     noio_pairs = world * reps * len(plan)
 
+    # ---- the storage + host-memory ceiling: the same file reads (into pinned memory) and writes (from pinned memory) with the
+    # same thread pools on all ranks at once, no GPU work, no host<->device copies
+    from concurrent.futures import ThreadPoolExecutor
+    ncpu = max(1, len(os.sched_getaffinity(0)) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
+    nthr = args.readers or max(2, min(8, ncpu // 2))
+    pool_r, pool_w = ThreadPoolExecutor(nthr), ThreadPoolExecutor(args.writers or nthr)
+    io_dir = os.path.join(args.root, "io_only%d" % rank)
+    os.makedirs(io_dir, exist_ok=True)
+    pin_fr = torch.empty((args.frames, args.h, args.w, 4), dtype=torch.float32).pin_memory().numpy()
+    pin_fl = torch.rand((npairs_seq, args.h, args.w, 2), dtype=torch.float32).pin_memory().numpy()
+    barrier()
+    t0 = time.perf_counter()
+    futs = []
+    for vi, (_, paths) in enumerate(mine):
+        futs += [pool_r.submit(flowio.read_tif_into, p, pin_fr[i]) for i, p in enumerate(paths)]
+        futs += [pool_w.submit(flowio.write_tif, os.path.join(io_dir, "%d_%d.tif" % (vi, k)), pin_fl[k]) for k in range(npairs_seq)]
+        if vi >= 1:                                      # keep about two videos of requests in flight, like the pipeline
+            for f in futs[:args.frames + npairs_seq]:
+                f.result()
+            futs = futs[args.frames + npairs_seq:]
+    for f in futs:
+        f.result()
+    io_s = max_over_ranks(time.perf_counter() - t0)
+    io_pairs = world * len(mine) * npairs_seq
+    pool_r.shutdown()
+    pool_w.shutdown()
+    shutil.rmtree(io_dir)
+
     # ---- spot check: a file of this rank against a direct device computation
     name, paths = mine[-1]
     fr = torch.from_numpy(np.stack([flowio.read_image(paths[i]) for i in (4, 5)])).cuda()
@@ -171,9 +199,13 @@ def main():
             "pairs_per_s_files_included": pairs / total_s, "seconds": total_s,
             "pairs_per_s_no_io_same_batches": noio_pairs / noio_s,
             "files_vs_no_io": (pairs / total_s) / (noio_pairs / noio_s),
+            "pairs_per_s_io_only_ceiling": io_pairs / io_s,
+            "files_vs_min_of_ceilings": (pairs / total_s) / min(noio_pairs / noio_s, io_pairs / io_s),
             "storage": args.root, "bare_read_GBps_1thread": read_gbs, "bare_write_GBps_1thread": write_gbs,
             "read_GBps_achieved_per_rank": stats.get("bytes_read", 0) / mine_s / 1e9,
             "write_GBps_achieved_per_rank": stats.get("bytes_written", 0) / mine_s / 1e9,
+            "rank0_waits_s": {k: round(stats.get(k, 0.0), 3) for k in ("wait_read_s", "wait_gpu_s", "wait_write_s")},
+            "rank0_seconds": mine_s,
             "readers": args.readers or "auto", "writers": args.writers or "auto", "batch_pairs": args.batch,
             "pinned_MB_per_rank": stats.get("pinned_bytes", 0) / 1e6, "host_cpus": os.cpu_count(),
             "host_binding": binding, "dataset_generation_s": gen_s, "files_bit_equal_to_direct_compute": ok,

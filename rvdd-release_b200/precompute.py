@@ -12,6 +12,7 @@ r, r+world, ... -- the pairs are independent, so there is no collective on the d
 list of files they wrote at the end.
 """
 import os
+import time
 
 import numpy as np
 
@@ -161,7 +162,9 @@ class _PipelinedGPU:
             from . import bridge as _b
             bridge = _b.default_bridge()
         self.torch, self.br = torch, bridge
+        # default pool sizes: the cores this process may use, shared with the other ranks of the node, half for each pool
         ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 4)
+        ncpu = max(1, ncpu // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
         self.readers = ThreadPoolExecutor(readers or max(2, min(8, ncpu // 2)), thread_name_prefix="rvdd-read")
         self.writers = ThreadPoolExecutor(writers or max(2, min(8, ncpu // 2)), thread_name_prefix="rvdd-write")
         self.sets = [_HostSet(torch) for _ in range(self.NHOST)]
@@ -170,14 +173,17 @@ class _PipelinedGPU:
         self.on_gpu = [None, None]                         # job per staging slot
         self.nsub = 0
         self.written = []
-        self.stats = dict(batches=0, pairs=0, frames_read=0, bytes_read=0, bytes_written=0)
+        self.stats = dict(batches=0, pairs=0, frames_read=0, bytes_read=0, bytes_written=0, wait_read_s=0.0, wait_gpu_s=0.0,
+                          wait_write_s=0.0)         # where the submitting thread waited: readers, the GPU, writers
 
     # ---- stage 1: read
     def _start_read(self, frame_paths, batch, want_warp):
         hs = self.sets[self.k % self.NHOST]
         self.k += 1
+        t0 = time.perf_counter()
         for f in hs.writes:                                # the files of the batch that used this set 4 batches ago
             f.result()
+        self.stats["wait_write_s"] += time.perf_counter() - t0
         hs.writes = []
         used = sorted({p["src"] for p in batch} | {p["tgt"] for p in batch})
         local = {f: i for i, f in enumerate(used)}
@@ -200,8 +206,10 @@ class _PipelinedGPU:
 
     # ---- stage 2: GPU
     def _submit(self, job, futs):
+        t0 = time.perf_counter()
         for f in futs:
             f.result()                                     # frames of this batch are in pinned memory
+        self.stats["wait_read_s"] += time.perf_counter() - t0
         slot = self.nsub & 1
         self.nsub += 1
         self._retire(slot)                                 # the batch submitted two steps ago on this slot
@@ -213,7 +221,9 @@ class _PipelinedGPU:
         job = self.on_gpu[slot]
         if job is None:
             return
+        t0 = time.perf_counter()
         self.br.wait_host(slot)
+        self.stats["wait_gpu_s"] += time.perf_counter() - t0
         self.on_gpu[slot] = None
         flow, warped = job["flow"].numpy(), (job["warped"].numpy() if job["warped"] is not None else None)
         for k, p in enumerate(job["batch"]):

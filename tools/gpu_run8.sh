@@ -1,5 +1,6 @@
+# usage: bash tools/gpu_run8.sh N [tag extra-args...]   (inside gpurun --gpus N)
+N=${1:-8}; TAG=${2:-auto}; shift; shift
 mkdir -p gpurun_out
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 5 --warmup 3 > gpurun_out/u_8gpu.json 2> gpurun_out/u_8gpu.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/u_2gpu.json 2> gpurun_out/u_2gpu.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 4 --steps 5 --warmup 3 > gpurun_out/u_4gpu.json 2> gpurun_out/u_4gpu.err
-grep -o '"value": [0-9.]*' gpurun_out/u_8gpu.json | head -1
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
+$TR profiles/bench_precompute.py --seqs-per-gpu 24 "$@" > gpurun_out/r2g_c4_${N}gpu_$TAG.json 2> gpurun_out/r2g_c4_${N}gpu_$TAG.err; tail -c 300 gpurun_out/r2g_c4_${N}gpu_$TAG.err
+cat gpurun_out/r2g_c4_${N}gpu_$TAG.json

@@ -187,6 +187,10 @@ struct rvdd_ctx {
     bool ws_used = false;
     long long spin_limit = 4000000000LL;        // solver watchdog in clock64 ticks (~2 s at 2 GHz); rvdd_set_watchdog
     int fuse_min_px = 0, fuse_first = 1;        // two-iterations-per-pass policy of the solver (RVDD_FUSE_MIN_PX / _FIRST)
+    // per-level CTA participation (RVDD_PX_PER_CTA): 0 = every CTA of a group works on every level.  Measured on B200 (one
+    // 1280x720 pair, 296 CTAs): 5.13 ms with all CTAs, 5.44 / 6.01 / 6.95 ms with one CTA per 768 / 1536 / 3072 pixels of a
+    // level -- the coarse levels are bound by the work per CTA and the staging latency, not by the size of the barrier.
+    int px_per_cta = 0;
 };
 
 static int create_resources(rvdd_ctx *c)
@@ -212,6 +216,7 @@ static int create_resources(rvdd_ctx *c)
     }
     if (const char *env = getenv("RVDD_FUSE_MIN_PX")) c->fuse_min_px = atoi(env);     // tuning / A-B runs only
     if (const char *env = getenv("RVDD_FUSE_FIRST")) c->fuse_first = atoi(env);
+    if (const char *env = getenv("RVDD_PX_PER_CTA")) c->px_per_cta = atoi(env);
     CK(cudaStreamCreateWithFlags(&c->st_compute, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking));
@@ -368,10 +373,11 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
     CK(c->pyr.ensure(sizeof(float) * (size_t)(2 * K) * P.total));
     CK(c->tmp.ensure(sizeof(float) * (size_t)(2 * K) * plane));
     CK(c->scratch.ensure(sizeof(float) * (size_t)G * scratch_stride));
-    // small: [slots 2K ints][status 32 ints][bar G*32 uints][partials G*4*C doubles]
+    // small: [slots 2K ints][status 32 ints][bar G*16*32 uints][mailbox G ints][partials G*4*C doubles]
     const size_t off_status = ((size_t)2 * K * sizeof(int) + 255) & ~(size_t)255;
     const size_t off_bar = off_status + 256;
-    const size_t off_part = (off_bar + (size_t)G * 32 * sizeof(unsigned) + 255) & ~(size_t)255;
+    const size_t nbar = (size_t)G * RVDD_MAX_SCALES * 32 + (size_t)G;        // barrier counters + mailboxes, zeroed together
+    const size_t off_part = (off_bar + nbar * sizeof(unsigned) + 255) & ~(size_t)255;
     CK(c->small.ensure(off_part + sizeof(double) * (size_t)G * 4 * C));
     CK(c->table.ensure(sizeof(void *) * (size_t)2 * K));
     char *small = (char *)c->small.p;
@@ -406,7 +412,7 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
 
     // ---- pyramid: normalise + presmooth (tvl1flow_lib.c:380-384), then zoom_out per level (:387-401)
     float *pyr = (float *)c->pyr.p, *tmp = (float *)c->tmp.p;
-    CK(launch_setup(slots, K, bar, G * 32, status, st));
+    CK(launch_setup(slots, K, bar, (int)nbar, status, st));
     CK(launch_minmax(dtab, dtab + K, nx * ny, K, slots, st));
     CK(launch_gauss(dtab, nullptr, 0, pyr, P.total, nx, ny, 2 * K, pre, slots, K, st));
     for (int s = 1; s < S; s++) {
@@ -452,6 +458,17 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
         A.scale_ns = (unsigned long long *)c->stamps.p;
     }
     A.bar = bar; A.partials = partials; A.status = status;
+    A.mailbox = (int *)(bar + (size_t)G * RVDD_MAX_SCALES * 32);
+    // CTAs per level: enough that each has about px_per_cta pixels of it (0 = everybody, always); never fewer than on the
+    // next coarser level
+    for (int s = S - 1; s >= 0; s--) {
+        long long n = (long long)P.nx[s] * P.ny[s];
+        int na = c->px_per_cta > 0 ? (int)((n + c->px_per_cta - 1) / c->px_per_cta) : C;
+        if (na < 1) na = 1;
+        if (na > C) na = C;
+        if (s + 1 < S && na < A.nact[s + 1]) na = A.nact[s + 1];
+        A.nact[s] = na;
+    }
     A.ngroups = G; A.ctas_per_group = C;
     A.spin_limit = c->spin_limit;
     A.fuse_min_px = c->fuse_min_px;

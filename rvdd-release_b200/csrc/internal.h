@@ -41,7 +41,9 @@ struct SolverArgs {
     long long scratch_stride, plane;    // plane = padded nx0*ny0
     int *iters_out;                     // [npairs][RVDD_MAX_SCALES][nwarps] or null
     float *err_out;                     // same shape, error at loop exit, or null
-    unsigned *bar;                      // [ngroups * 32] (one counter per 128 B)
+    unsigned *bar;                      // [ngroups][RVDD_MAX_SCALES][32]: one barrier counter per group and level, 128 B apart
+    int *mailbox;                       // [ngroups]: buffer parities handed from a level's leader to the next level's CTAs
+    int nact[RVDD_MAX_SCALES];          // CTAs of a group that take part in level s (non-increasing with s)
     double *partials;                   // [ngroups][2 slots][2 sums][ctas_per_group]
     unsigned long long *scale_ns;       // optional [npairs][RVDD_MAX_SCALES + 1] globaltimer stamps (profiling)
     int *status;                        // [0]: watchdog flag

@@ -57,6 +57,22 @@ for (B, C, H, W) in [(1, 3, 1440, 2560), (1, 48, 1440, 2560), (4, 48, 720, 1280)
                      ms_fused_up2=t_half, ms_white_noise_flow=t_rough, ms_torch_grid_sample=t_ref))
     print(json.dumps(rows[-1]))
 
+# (H, W, 4) frames in their on-disk layout (channel innermost): the warp of the headline step (compute_flow_and_warp)
+for (B, C, H, W) in [(29, 4, 720, 1280), (8, 4, 1080, 1920)]:
+    x = torch.randn(B, H, W, C, device="cuda").permute(0, 3, 1, 2)
+    yy, xx = torch.meshgrid(torch.arange(H, device="cuda", dtype=torch.float32), torch.arange(W, device="cuda", dtype=torch.float32), indexing="ij")
+    flow = torch.stack((5.0 + 3.0 * torch.sin(yy / 97.0), -3.0 + 2.0 * torch.cos(xx / 131.0)), 0)[None].repeat(B, 1, 1, 1).contiguous()
+    flow += 0.05 * torch.randn_like(flow)
+    rough = 3.0 * torch.randn(B, 2, H, W, device="cuda")
+    out = torch.empty(B, H, W, C, device="cuda").permute(0, 3, 1, 2)
+    by = 4.0 * B * H * W * (2 * C + 2)
+    t_full = timeit(lambda: br.warp(x, flow, "bicubic", want_mask=False, out=out))
+    t_rough = timeit(lambda: br.warp(x, rough, "bicubic", want_mask=False, out=out))
+    t_bil = timeit(lambda: br.warp(x, flow, "bilinear", want_mask=False, out=out))
+    rows.append(dict(layout="HWC", shape=[B, C, H, W], ms=t_full, gbs=by / t_full / 1e6, frac=by / t_full / 1e6 / peak,
+                     ms_white_noise_flow=t_rough, ms_bilinear=t_bil, tma=bool(os.environ.get("RVDD_WARP_TMA"))))
+    print(json.dumps(rows[-1]))
+
 # Hamilton-Adams demosaic (csrc/demosaic.cu): 4 B read + 12 B written per full-resolution pixel
 for (B, H, W) in [(1, 720, 1280), (8, 720, 1280), (1, 1080, 1920)]:
     x = torch.rand(B, 4, H, W, device="cuda") * 2 - 1

@@ -187,10 +187,6 @@ struct rvdd_ctx {
     bool ws_used = false;
     long long spin_limit = 4000000000LL;        // solver watchdog in clock64 ticks (~2 s at 2 GHz); rvdd_set_watchdog
     int fuse_min_px = 0, fuse_first = 1;        // two-iterations-per-pass policy of the solver (RVDD_FUSE_MIN_PX / _FIRST)
-    // per-level CTA participation (RVDD_PX_PER_CTA): 0 = every CTA of a group works on every level.  Measured on B200 (one
-    // 1280x720 pair, 296 CTAs): 5.13 ms with all CTAs, 5.44 / 6.01 / 6.95 ms with one CTA per 768 / 1536 / 3072 pixels of a
-    // level -- the coarse levels are bound by the work per CTA and the staging latency, not by the size of the barrier.
-    int px_per_cta = 0;
 };
 
 static int create_resources(rvdd_ctx *c)
@@ -216,7 +212,6 @@ static int create_resources(rvdd_ctx *c)
     }
     if (const char *env = getenv("RVDD_FUSE_MIN_PX")) c->fuse_min_px = atoi(env);     // tuning / A-B runs only
     if (const char *env = getenv("RVDD_FUSE_FIRST")) c->fuse_first = atoi(env);
-    if (const char *env = getenv("RVDD_PX_PER_CTA")) c->px_per_cta = atoi(env);
     CK(cudaStreamCreateWithFlags(&c->st_compute, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking));
@@ -303,24 +298,37 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// scratch viewed as [nplanes][plane] floats; box = `box_planes` adjacent planes x 136 consecutive floats
-static int encode_scratch_map(CUtensorMap *tm, float *scratch, long long plane, long long nplanes, int box_planes)
+// 2-D float32 tensor map: dims (d0 innermost, d1), row pitch in bytes, box (b0, b1); out-of-range elements read as zero
+namespace rvdd {
+cudaError_t encode_map_2d(CUtensorMap *tm, const float *base, unsigned long long d0, unsigned long long d1,
+                          unsigned long long pitch_bytes, unsigned b0, unsigned b1)
 {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void *p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p)
-            return fail("cuTensorMapEncodeTiled not available from this driver");
+            return cudaErrorNotSupported;
         fn = (EncodeTiledFn)p;
     }
-    const cuuint64_t dims[2] = {(cuuint64_t)plane, (cuuint64_t)nplanes};
-    const cuuint64_t strides[1] = {(cuuint64_t)plane * sizeof(float)};
-    const cuuint32_t box[2] = {136u, (cuuint32_t)box_planes};
+    const cuuint64_t dims[2] = {(cuuint64_t)d0, (cuuint64_t)d1};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)b0, (cuuint32_t)b1};
     const cuuint32_t estr[2] = {1u, 1u};
-    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, scratch, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed");
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+}  // namespace rvdd
+
+// scratch viewed as [nplanes][plane] floats; box = `box_planes` adjacent planes x 136 consecutive floats
+static int encode_scratch_map(CUtensorMap *tm, float *scratch, long long plane, long long nplanes, int box_planes)
+{
+    const cudaError_t e = encode_map_2d(tm, scratch, (unsigned long long)plane, (unsigned long long)nplanes,
+                                        (unsigned long long)plane * sizeof(float), 136u, (unsigned)box_planes);
+    if (e == cudaErrorNotSupported) return fail("cuTensorMapEncodeTiled not available from this driver");
+    if (e != cudaSuccess) return fail("cuTensorMapEncodeTiled failed");
     return 0;
 }
 
@@ -373,10 +381,10 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
     CK(c->pyr.ensure(sizeof(float) * (size_t)(2 * K) * P.total));
     CK(c->tmp.ensure(sizeof(float) * (size_t)(2 * K) * plane));
     CK(c->scratch.ensure(sizeof(float) * (size_t)G * scratch_stride));
-    // small: [slots 2K ints][status 32 ints][bar G*16*32 uints][mailbox G ints][partials G*4*C doubles]
+    // small: [slots 2K ints][status 32 ints][bar G*32 uints][partials G*4*C doubles]
     const size_t off_status = ((size_t)2 * K * sizeof(int) + 255) & ~(size_t)255;
     const size_t off_bar = off_status + 256;
-    const size_t nbar = (size_t)G * RVDD_MAX_SCALES * 32 + (size_t)G;        // barrier counters + mailboxes, zeroed together
+    const size_t nbar = (size_t)G * 32;
     const size_t off_part = (off_bar + nbar * sizeof(unsigned) + 255) & ~(size_t)255;
     CK(c->small.ensure(off_part + sizeof(double) * (size_t)G * 4 * C));
     CK(c->table.ensure(sizeof(void *) * (size_t)2 * K));
@@ -458,17 +466,6 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
         A.scale_ns = (unsigned long long *)c->stamps.p;
     }
     A.bar = bar; A.partials = partials; A.status = status;
-    A.mailbox = (int *)(bar + (size_t)G * RVDD_MAX_SCALES * 32);
-    // CTAs per level: enough that each has about px_per_cta pixels of it (0 = everybody, always); never fewer than on the
-    // next coarser level
-    for (int s = S - 1; s >= 0; s--) {
-        long long n = (long long)P.nx[s] * P.ny[s];
-        int na = c->px_per_cta > 0 ? (int)((n + c->px_per_cta - 1) / c->px_per_cta) : C;
-        if (na < 1) na = 1;
-        if (na > C) na = C;
-        if (s + 1 < S && na < A.nact[s + 1]) na = A.nact[s + 1];
-        A.nact[s] = na;
-    }
     A.ngroups = G; A.ctas_per_group = C;
     A.spin_limit = c->spin_limit;
     A.fuse_min_px = c->fuse_min_px;

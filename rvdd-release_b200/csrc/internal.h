@@ -41,9 +41,7 @@ struct SolverArgs {
     long long scratch_stride, plane;    // plane = padded nx0*ny0
     int *iters_out;                     // [npairs][RVDD_MAX_SCALES][nwarps] or null
     float *err_out;                     // same shape, error at loop exit, or null
-    unsigned *bar;                      // [ngroups][RVDD_MAX_SCALES][32]: one barrier counter per group and level, 128 B apart
-    int *mailbox;                       // [ngroups]: buffer parities handed from a level's leader to the next level's CTAs
-    int nact[RVDD_MAX_SCALES];          // CTAs of a group that take part in level s (non-increasing with s)
+    unsigned *bar;                      // [ngroups * 32] (one counter per 128 B)
     double *partials;                   // [ngroups][2 slots][2 sums][ctas_per_group]
     unsigned long long *scale_ns;       // optional [npairs][RVDD_MAX_SCALES + 1] globaltimer stamps (profiling)
     int *status;                        // [0]: watchdog flag
@@ -52,6 +50,10 @@ struct SolverArgs {
     int fuse_min_px;                    // levels with at least this many pixels (and nx % 4 == 0) run two iterations per pass
     int fuse_first;                     // ... after this many single iterations of every inner loop
 };
+
+// bridge.cu: 2-D float32 TMA descriptor (dims d0 innermost / d1, row pitch in bytes, box b0 x b1, zero fill out of range)
+cudaError_t encode_map_2d(CUtensorMap *tm, const float *base, unsigned long long d0, unsigned long long d1,
+                          unsigned long long pitch_bytes, unsigned b0, unsigned b1);
 
 // prep.cu
 cudaError_t launch_setup(int *minmax_slots, int npairs, unsigned *bar, int nbar, int *status, cudaStream_t st);

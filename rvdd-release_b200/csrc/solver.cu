@@ -44,7 +44,8 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
 }
 
 struct GroupCtx {
-    unsigned *bar;          // this group's counters: one per pyramid level, 32 words (128 B) apart
+    unsigned *bar;          // this group's counter
+    unsigned target;        // value the counter reaches when everybody has arrived (thread 0 only)
     int nctas, cta;         // group size, rank inside the group
     double *partials;       // [2 slots][2 sums][nctas]
     int *status;
@@ -52,24 +53,19 @@ struct GroupCtx {
     int slot;
 };
 
-// Barrier among the `nact` CTAs that take part in pyramid level `level` (the CTAs with the lowest ranks of the group).  Every
-// level has its own monotonic counter and its own running target (s_target, used by thread 0), so a CTA that sits a coarse
-// level out does not have to know how many data-dependent barriers that level needed: it simply arrives early at the first
-// barrier of the next level it belongs to and waits there for the others.
 // Returns false if the watchdog fired (somebody waited longer than spin_limit): the kernel then unwinds.
-__device__ __forceinline__ bool group_sync(GroupCtx &g, int level, int nact, unsigned *s_target, int *s_flag)
+__device__ __forceinline__ bool group_sync(GroupCtx &g, int *s_flag)
 {
     asm volatile("fence.proxy.async;" ::: "memory");   // this thread's stores may next be read by bulk async copies
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned *bar = g.bar + level * 32;
-        const unsigned target = (s_target[level] += (unsigned)nact);
+        g.target += (unsigned)g.nctas;
         __threadfence();
-        atomicAdd(bar, 1u);
+        atomicAdd(g.bar, 1u);
         const long long t0 = clock64();
         int dead = 0;
         unsigned spins = 0;
-        while ((int)(ld_acquire_u32(bar) - target) < 0) {
+        while ((int)(ld_acquire_u32(g.bar) - g.target) < 0) {
             if ((spins & 1023u) == 0) {      // the clock is looked at on the first unsuccessful poll, then every 1024
                 if (spins && *(volatile int *)g.status != 0) { dead = 1; break; }
                 if (clock64() - t0 > g.spin_limit) { atomicExch(g.status, 1); dead = 1; break; }
@@ -85,12 +81,12 @@ __device__ __forceinline__ bool group_sync(GroupCtx &g, int level, int nact, uns
 }
 
 // Sum of the per-CTA residual partials of this group, in a fixed order (deterministic, identical in every CTA).
-__device__ __forceinline__ double group_sum(const GroupCtx &g, int slot, int nact, double *s_val)
+__device__ __forceinline__ double group_sum(const GroupCtx &g, int slot, double *s_val)
 {
     if (threadIdx.x < 32) {
         double acc = 0.0;
         const double *p = g.partials + (size_t)slot * g.nctas;
-        for (int i = threadIdx.x; i < nact; i += 32) acc += __ldcg(p + i);
+        for (int i = threadIdx.x; i < g.nctas; i += 32) acc += __ldcg(p + i);
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (threadIdx.x == 0) *s_val = acc;
     }
@@ -674,7 +670,6 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
     __shared__ double s_red[SOLVER_WARPS], s_red2[SOLVER_WARPS];
     __shared__ double s_val, s_val2;
     __shared__ int s_flag;
-    __shared__ unsigned s_target[RVDD_MAX_SCALES];
     extern __shared__ __align__(128) unsigned char s_dyn[];
 
     // per-warp staging ring for the bulk-copy row pipeline
@@ -692,17 +687,18 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
     GroupCtx g;
     g.nctas = A.ctas_per_group;
     g.cta = blockIdx.x - group * A.ctas_per_group;
-    g.bar = A.bar + (size_t)group * RVDD_MAX_SCALES * 32;
+    g.bar = A.bar + group * 32;
+    g.target = 0u;
     g.partials = A.partials + (size_t)group * 4 * A.ctas_per_group;
     g.status = A.status;
     g.spin_limit = A.spin_limit;
     g.slot = 0;
-    if (threadIdx.x < RVDD_MAX_SCALES) s_target[threadIdx.x] = 0u;
-    __syncthreads();
     if (group >= A.ngroups) return;
 
+    const int gthreads = g.nctas * SOLVER_THREADS;
     const int gtid = g.cta * SOLVER_THREADS + threadIdx.x;
     const int gwarp = g.cta * SOLVER_WARPS + (threadIdx.x >> 5);
+    const int gwarps = g.nctas * SOLVER_WARPS;
 
     // per-group scratch planes
     float *S = A.scratch + (long long)group * A.scratch_stride;
@@ -730,56 +726,19 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
         int uc = 0, pc = 0;
 
         for (int s = A.S - 1; s >= 0; s--) {
-            // ---- who works on this level: the first nact CTAs of the group (A.nact is non-increasing with s: every CTA of a
-            // level also works on all finer ones).  Small levels are latency-bound -- a barrier among few CTAs is much
-            // cheaper than one among all, and the others wait at the first barrier of the first level they belong to.
-            const int nact = A.nact[s];
-            if (g.cta >= nact) continue;
-            const int gthreads = nact * SOLVER_THREADS, gwarps = nact * SOLVER_WARPS;
-            if (stamping) {
-                A.scale_ns[(long long)pair * (RVDD_MAX_SCALES + 1) + s] = now_ns();
+            if (A.scale_ns && g.cta == 0 && threadIdx.x == 0) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                A.scale_ns[(long long)pair * (RVDD_MAX_SCALES + 1) + s] = t;
                 if (s == 0) A.scale_ns[(long long)pair * (RVDD_MAX_SCALES + 1) + RVDD_MAX_SCALES] = 0ULL;
             }
             const int nx = A.nx[s], ny = A.ny[s], n = nx * ny;
             const float *I0 = P0 + A.off[s], *I1 = P1 + A.off[s];
-            g.slot = 0;      // residual-partial double buffer: CTAs that sat coarser levels out must agree with the others
 
             if (s == A.S - 1) {
                 // ---- flow = 0 at the coarsest scale (:404-405)
                 for (int i = gtid; i < n; i += gthreads) { UB(uc, 0)[i] = 0.f; UB(uc, 1)[i] = 0.f; }
-            } else {
-                // ---- level s + 1 is complete once its CTAs (a subset of this level's) have arrived here; its leader left the
-                // buffer parities in the group's mailbox
-                if (!group_sync(g, s, nact, s_target, &s_flag)) return;
-                const int mail = __ldcg(A.mailbox + group);
-                uc = mail & 1;
-                pc = (mail >> 1) & 1;
-                // ---- zoom_in from level s + 1 and rescale (:425-433, zoom.c:85-109)
-                const int cx_n = A.nx[s + 1], cy_n = A.ny[s + 1], cn = cx_n * cy_n;
-                const float *c1 = UB(uc, 0), *c2 = UB(uc, 1);
-                float *f1 = UB(uc ^ 1, 0), *f2 = UB(uc ^ 1, 1);
-                const float zx = A.zfx[s], zy = A.zfy[s];
-                if (nx == 2 * cx_n && ny == 2 * cy_n) {
-                    // exact factor 2: one thread per coarse pixel writes its 2x2 fine block (shared taps, zero fractions)
-                    for (int i = gtid; i < cn; i += gthreads) {
-                        const int Y = i / cx_n, X = i - Y * cx_n;
-                        float b1[2][2], b2[2][2];
-                        zoom_in_2x_block(c1, X, Y, cx_n, cy_n, A.zoom_mul, b1);
-                        zoom_in_2x_block(c2, X, Y, cx_n, cy_n, A.zoom_mul, b2);
-                        const long long o = (long long)(2 * Y) * nx + 2 * X;
-                        *reinterpret_cast<float2 *>(f1 + o) = make_float2(b1[0][0], b1[0][1]);
-                        *reinterpret_cast<float2 *>(f1 + o + nx) = make_float2(b1[1][0], b1[1][1]);
-                        *reinterpret_cast<float2 *>(f2 + o) = make_float2(b2[0][0], b2[0][1]);
-                        *reinterpret_cast<float2 *>(f2 + o + nx) = make_float2(b2[1][0], b2[1][1]);
-                    }
-                } else {
-                    for (int i = gtid; i < n; i += gthreads) {
-                        const int y = i / nx, x = i - y * nx;
-                        f1[i] = zoom_in_px(c1, x, y, cx_n, cy_n, zx, zy, A.zoom_mul);
-                        f2[i] = zoom_in_px(c2, x, y, cx_n, cy_n, zx, zy, A.zoom_mul);
-                    }
-                }
-                uc ^= 1;
+                if (s < A.fscale && !group_sync(g, &s_flag)) return;
             }
             if (s >= A.fscale) {
                 // ---- per-scale setup: p = 0 (:134-138), centred gradient of I1 (:131, mask.c:149-206)
@@ -788,7 +747,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
                     PB(pc, 0)[i] = 0.f; PB(pc, 1)[i] = 0.f; PB(pc, 2)[i] = 0.f; PB(pc, 3)[i] = 0.f;
                     cgrad_px(I1, x, y, nx, ny, &I1x[i], &I1y[i]);
                 }
-                if (!group_sync(g, s, nact, s_target, &s_flag)) return;
+                if (!group_sync(g, &s_flag)) return;
 
                 unsigned long long ns_consts = 0ULL, ns_iter = 0ULL;
                 for (int w = 0; w < A.nwarps; w++) {
@@ -796,13 +755,13 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
                     // ---- warp constants (:143-159): bicubic samples of I1, I1x, I1y at x + u
                     const float *u1 = UB(uc, 0), *u2 = UB(uc, 1);
                     warp_consts_group(I0, I1, I1x, I1y, u1, u2, gx, gy, rc, nx, ny, gwarp, gwarps);
-                    if (!group_sync(g, s, nact, s_target, &s_flag)) return;
+                    if (!group_sync(g, &s_flag)) return;
                     const unsigned long long tp1 = stamping ? now_ns() : 0ULL;
 
-                    // ---- inner loop (:161-244), stop test after every iteration.  (-DRVDD_FUSE2: big levels run the first
-                    // iteration alone and then TWO iterations per pass, iterate2_strip_tma: both residuals come back, and if
-                    // the first of the two already met the stopping rule that iteration is replayed alone from the input
-                    // buffers, which the fused pass leaves untouched.)
+                    // ---- inner loop (:161-244), stop test after every iteration.  Big levels run the first iteration alone
+                    // (many loops stop right there) and then TWO iterations per pass (iterate2_strip_tma): both residuals
+                    // come back, and if the first of the two already met the stopping rule that iteration is replayed
+                    // alone from the input buffers, which the fused pass leaves untouched.
                     int it = 0;
                     float err = INFINITY;
 #if defined(RVDD_FUSE2)
@@ -835,9 +794,9 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
                             g.partials[(size_t)(2 * g.slot) * g.nctas + g.cta] = t;
                             g.partials[(size_t)(2 * g.slot + 1) * g.nctas + g.cta] = t2;
                         }
-                        if (!group_sync(g, s, nact, s_target, &s_flag)) return;
-                        const double tot = group_sum(g, 2 * g.slot, nact, &s_val);
-                        const double tot2 = fused ? group_sum(g, 2 * g.slot + 1, nact, &s_val2) : 0.0;
+                        if (!group_sync(g, &s_flag)) return;
+                        const double tot = group_sum(g, 2 * g.slot, &s_val);
+                        const double tot2 = fused ? group_sum(g, 2 * g.slot + 1, &s_val2) : 0.0;
                         g.slot ^= 1;
                         err = FDIV((float)tot, (float)n);        // error /= size (:223)
                         if (!fused) {
@@ -847,7 +806,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
                             err = FDIV((float)tot2, (float)n);
                         } else {                                 // the reference stops after iteration A: replay it alone
                             iterate_group<4>(A, group, P, T, nx, ny, K, gwarp, gwarps, A.status);
-                            if (!group_sync(g, s, nact, s_target, &s_flag)) return;
+                            if (!group_sync(g, &s_flag)) return;
                             it++;
                         }
                         uc ^= 1;
@@ -873,17 +832,44 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
             }
 
             if (s > 0) {
-                // ---- hand over to the next finer level: its CTAs read the buffer parities after their first barrier
-                if (g.cta == 0 && threadIdx.x == 0) A.mailbox[group] = uc | (pc << 1);
+                // ---- zoom_in to the next finer level and rescale (:425-433, zoom.c:85-109)
+                const int fx_n = A.nx[s - 1], fy_n = A.ny[s - 1], fn = fx_n * fy_n;
+                const float *c1 = UB(uc, 0), *c2 = UB(uc, 1);
+                float *f1 = UB(uc ^ 1, 0), *f2 = UB(uc ^ 1, 1);
+                const float zx = A.zfx[s - 1], zy = A.zfy[s - 1];
+                if (fx_n == 2 * nx && fy_n == 2 * ny) {
+                    // exact factor 2: one thread per coarse pixel writes its 2x2 fine block (shared taps, zero fractions)
+                    for (int i = gtid; i < n; i += gthreads) {
+                        const int Y = i / nx, X = i - Y * nx;
+                        float b1[2][2], b2[2][2];
+                        zoom_in_2x_block(c1, X, Y, nx, ny, A.zoom_mul, b1);
+                        zoom_in_2x_block(c2, X, Y, nx, ny, A.zoom_mul, b2);
+                        const long long o = (long long)(2 * Y) * fx_n + 2 * X;
+                        *reinterpret_cast<float2 *>(f1 + o) = make_float2(b1[0][0], b1[0][1]);
+                        *reinterpret_cast<float2 *>(f1 + o + fx_n) = make_float2(b1[1][0], b1[1][1]);
+                        *reinterpret_cast<float2 *>(f2 + o) = make_float2(b2[0][0], b2[0][1]);
+                        *reinterpret_cast<float2 *>(f2 + o + fx_n) = make_float2(b2[1][0], b2[1][1]);
+                    }
+                } else {
+                    for (int i = gtid; i < fn; i += gthreads) {
+                        const int y = i / fx_n, x = i - y * fx_n;
+                        f1[i] = zoom_in_px(c1, x, y, nx, ny, zx, zy, A.zoom_mul);
+                        f2[i] = zoom_in_px(c2, x, y, nx, ny, zx, zy, A.zoom_mul);
+                    }
+                }
+                uc ^= 1;
             } else {
                 // ---- finest flow -> caller's planar (u, v) buffer (:374-375)
                 float *o1 = A.flow_out + (long long)pair * 2 * n, *o2 = o1 + n;
                 const float *c1 = UB(uc, 0), *c2 = UB(uc, 1);
                 for (int i = gtid; i < n; i += gthreads) { o1[i] = c1[i]; o2[i] = c2[i]; }
-                if (stamping) A.scale_ns[(long long)pair * (RVDD_MAX_SCALES + 1) + RVDD_MAX_SCALES] = now_ns();
-                // end of the pair: the group's scratch planes are free again
-                if (!group_sync(g, 0, nact, s_target, &s_flag)) return;
+                if (A.scale_ns && g.cta == 0 && threadIdx.x == 0) {
+                    unsigned long long t;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                    A.scale_ns[(long long)pair * (RVDD_MAX_SCALES + 1) + RVDD_MAX_SCALES] = t;
+                }
             }
+            if (!group_sync(g, &s_flag)) return;
         }
     }
 }

@@ -9,6 +9,8 @@
 // un-normalise ((g+1)/2)*(W-1), bicubic = Keys A=-0.75 with the centre left unclipped and every tap clamped to
 // the image, bilinear = centre clipped to the border first.  Results agree with torch to ~1e-6 relative (the
 // float expression order of the two ATen back ends differs by that much already); the gate is 1e-4.
+#include <stdlib.h>
+
 #include "internal.h"
 
 namespace rvdd {
@@ -378,12 +380,178 @@ __global__ void __launch_bounds__(256) warp_hwc4_kernel(const WarpArgs a)
     }
 }
 
+// ------------------------------------------------------------------------------------------------ HWC, 4 channels, TMA-staged
+//
+// OPT-IN (environment RVDD_WARP_TMA=1): measured SLOWER than the L1 gathers of warp_hwc4_kernel on B200 -- 29 x (720, 1280, 4):
+// 0.53 ms against 0.43 ms, also with smaller boxes (40 x 14: 0.53 ms, 36 x 12: 0.57 ms; profiles/stage_kernels_r02.jsonl).
+// The per-tile chain flow -> bounding box -> TMA request -> wait -> gather is serial inside a CTA and eight resident CTAs do
+// not hide it, while the direct kernel keeps 16 independent 128-bit loads per thread in flight.  Kept as the measured
+// alternative (and parity-tested), not as the default.
+//
+// Same job as warp_hwc4_kernel, but the taps do not come through L1 (16 tag look-ups per pixel, 83 % hits, the misses at
+// L2 latency): the bounding box of the 32x8 tile's taps is fetched ONCE by the TMA unit -- cp.async.bulk.tensor.2d over the
+// frames viewed as a [B*H rows][W*4 floats] tensor, a box of WH_BW pixels x WH_BH rows landing in shared memory in exactly
+// the channel-interleaved layout the gather wants (one pixel = one float4) -- and the 16 taps of a pixel are 16 conflict-free
+// 128-bit shared loads.  No thread issues a global load for the frames at all.  A tile whose flow spreads the taps over more
+// than the box (or frames that are not densely packed) takes the direct-gather kernel's path.  Same arithmetic.
+#ifndef WH_BW
+#define WH_BW 48
+#endif
+#ifndef WH_BH
+#define WH_BH 24
+#endif
+
+template <int INTERP>
+__global__ void __launch_bounds__(256) warp_hwc4_tma_kernel(const WarpArgs a, const __grid_constant__ CUtensorMap tm)
+{
+    __shared__ __align__(128) float4 s_box[WH_BH * WH_BW];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ int s_lim[4];
+    const int lane = threadIdx.x & 31;
+    const int x = blockIdx.x * 32 + lane, y = blockIdx.y * 8 + (threadIdx.x >> 5), b = blockIdx.z;
+    const bool inside = (x < a.W && y < a.H);
+    if (threadIdx.x == 0) {
+        s_lim[0] = 0x7fffffff; s_lim[1] = -0x7fffffff; s_lim[2] = 0x7fffffff; s_lim[3] = -0x7fffffff;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&s_bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    float ix = 0.f, iy = 0.f;
+    if (inside) {
+        float fu, fv;
+        const float *fl = a.flow + (long long)b * 2 * a.fh * a.fw;
+        if (a.fh == a.H && a.fw == a.W) {
+            fu = fl[(long long)y * a.W + x];
+            fv = fl[(long long)a.H * a.W + (long long)y * a.W + x];
+        } else {
+            const float sy = a.H > 1 ? (float)(a.fh - 1) / (float)(a.H - 1) : 0.f;
+            const float sx = a.W > 1 ? (float)(a.fw - 1) / (float)(a.W - 1) : 0.f;
+            fu = up2_sample(fl, a.fh, a.fw, y, x, sy, sx);
+            fv = up2_sample(fl + (long long)a.fh * a.fw, a.fh, a.fw, y, x, sy, sx);
+        }
+        fu *= a.flow_mul;
+        fv *= a.flow_mul;
+        const float gxn = 2.0f * ((float)x + fu) / (float)(a.W - 1) - 1.0f;
+        const float gyn = 2.0f * ((float)y + fv) / (float)(a.H - 1) - 1.0f;
+        if (a.mask)
+            a.mask[((long long)b * a.H + y) * a.W + x] = (gxn >= -1.f && gxn <= 1.f && gyn >= -1.f && gyn <= 1.f) ? 1.f : 0.f;
+        ix = ((gxn + 1.f) / 2.f) * (float)(a.W - 1);
+        iy = ((gyn + 1.f) / 2.f) * (float)(a.H - 1);
+    }
+    constexpr int NT = (INTERP == 1) ? 4 : 2;
+    float cx[NT], cy[NT];
+    int tx[NT], ty[NT];
+    if (INTERP == 1) {
+        const float fx0 = floorf(ix), fy0 = floorf(iy);
+        float wx[4], wyy[4];
+        cubic_coeffs(ix - fx0, wx);
+        cubic_coeffs(iy - fy0, wyy);
+#pragma unroll
+        for (int k = 0; k < NT; k++) {
+            cx[k] = wx[k];
+            cy[k] = wyy[k];
+            tx[k] = (int)fminf((float)(a.W - 1), fmaxf(fx0 - 1.f + (float)k, 0.f));
+            ty[k] = (int)fminf((float)(a.H - 1), fmaxf(fy0 - 1.f + (float)k, 0.f));
+        }
+    } else {
+        ix = fminf((float)(a.W - 1), fmaxf(ix, 0.f));
+        iy = fminf((float)(a.H - 1), fmaxf(iy, 0.f));
+        const float fx0 = floorf(ix), fy0 = floorf(iy);
+        tx[0] = (int)fx0; ty[0] = (int)fy0;
+        tx[NT - 1] = min(tx[0] + 1, a.W - 1); ty[NT - 1] = min(ty[0] + 1, a.H - 1);
+        cx[NT - 1] = ix - fx0; cy[NT - 1] = iy - fy0;
+        cx[0] = 1.f - cx[NT - 1]; cy[0] = 1.f - cy[NT - 1];
+    }
+    __syncthreads();
+    {
+        int lox = inside ? tx[0] : 0x7fffffff, hix = inside ? tx[NT - 1] : -0x7fffffff;
+        int loy = inside ? ty[0] : 0x7fffffff, hiy = inside ? ty[NT - 1] : -0x7fffffff;
+        lox = __reduce_min_sync(0xffffffffu, lox); hix = __reduce_max_sync(0xffffffffu, hix);
+        loy = __reduce_min_sync(0xffffffffu, loy); hiy = __reduce_max_sync(0xffffffffu, hiy);
+        if (lane == 0) { atomicMin(&s_lim[0], lox); atomicMax(&s_lim[1], hix); atomicMin(&s_lim[2], loy); atomicMax(&s_lim[3], hiy); }
+    }
+    __syncthreads();
+    const int bx0 = s_lim[0], by0 = s_lim[2], bw = s_lim[1] - s_lim[0] + 1, bh = s_lim[3] - s_lim[2] + 1;
+    const bool staged = (bw <= WH_BW && bh <= WH_BH);      // block-uniform
+    float *ob = a.out + (long long)b * a.os_b + (long long)y * a.os_h + (long long)x * a.os_w;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (staged) {
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)(WH_BW * WH_BH * 16)) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                             (unsigned)__cvta_generic_to_shared(s_box)),
+                         "l"(&tm), "r"(bx0 * 4), "r"(b * a.H + by0), "r"(bar)
+                         : "memory");
+        }
+        unsigned ok = 0;
+        while (!ok)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(bar) : "memory");
+        if (!inside) return;
+#pragma unroll
+        for (int r = 0; r < NT; r++) {
+            const float4 *q = s_box + (ty[r] - by0) * WH_BW - bx0;
+            float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (INTERP == 1) {
+                const float4 v0 = q[tx[0]], v1 = q[tx[1]], v2 = q[tx[NT - 2]], v3 = q[tx[NT - 1]];
+                row.x = v0.x * cx[0] + v1.x * cx[1] + v2.x * cx[NT - 2] + v3.x * cx[NT - 1];
+                row.y = v0.y * cx[0] + v1.y * cx[1] + v2.y * cx[NT - 2] + v3.y * cx[NT - 1];
+                row.z = v0.z * cx[0] + v1.z * cx[1] + v2.z * cx[NT - 2] + v3.z * cx[NT - 1];
+                row.w = v0.w * cx[0] + v1.w * cx[1] + v2.w * cx[NT - 2] + v3.w * cx[NT - 1];
+                acc.x += row.x * cy[r]; acc.y += row.y * cy[r]; acc.z += row.z * cy[r]; acc.w += row.w * cy[r];
+            } else {
+                const float4 v0 = q[tx[0]], v1 = q[tx[NT - 1]];
+                const float w0 = cx[0] * cy[r], w1 = cx[NT - 1] * cy[r];
+                if (r == 0) {
+                    acc.x = v0.x * w0 + v1.x * w1; acc.y = v0.y * w0 + v1.y * w1; acc.z = v0.z * w0 + v1.z * w1; acc.w = v0.w * w0 + v1.w * w1;
+                } else {
+                    acc.x = acc.x + v0.x * w0 + v1.x * w1; acc.y = acc.y + v0.y * w0 + v1.y * w1;
+                    acc.z = acc.z + v0.z * w0 + v1.z * w1; acc.w = acc.w + v0.w * w0 + v1.w * w1;
+                }
+            }
+        }
+    } else {
+        if (!inside) return;
+        const float4 *xb = reinterpret_cast<const float4 *>(a.x + (long long)b * a.xs_b);
+        const long long rowq = a.xs_h >> 2;
+#pragma unroll
+        for (int r = 0; r < NT; r++) {
+            const float4 *q = xb + (long long)ty[r] * rowq;
+            float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < NT; k++) {
+                const float4 v = __ldg(q + tx[k]);
+                row.x += v.x * cx[k]; row.y += v.y * cx[k]; row.z += v.z * cx[k]; row.w += v.w * cx[k];
+            }
+            acc.x += row.x * cy[r]; acc.y += row.y * cy[r]; acc.z += row.z * cy[r]; acc.w += row.w * cy[r];
+        }
+    }
+    if (a.os_c == 1 && ((reinterpret_cast<uintptr_t>(ob) & 15) == 0)) {
+        *reinterpret_cast<float4 *>(ob) = acc;
+    } else {
+        ob[0] = acc.x; ob[a.os_c] = acc.y; ob[2 * a.os_c] = acc.z; ob[3 * a.os_c] = acc.w;
+    }
+}
+
 cudaError_t launch_warp(const WarpArgs &a, cudaStream_t st)
 {
     if (a.B <= 0 || a.C <= 0 || a.H <= 0 || a.W <= 0) return cudaSuccess;
     dim3 grid((a.W + 31) / 32, (a.H + 7) / 8, a.B);
     if (a.C == 4 && a.xs_c == 1 && a.xs_w == 4 && (a.xs_h & 3) == 0 && (a.xs_b & 3) == 0 &&
         (reinterpret_cast<uintptr_t>(a.x) & 15) == 0) {   // channel-innermost 4-channel frames: 128-bit gathers
+        // densely packed frames: the TMA-staged kernel (one tensor map over [B * H rows][W * 4 floats])
+        if (a.xs_h == (long long)a.W * 4 && a.xs_b == (long long)a.H * a.W * 4 && a.W * 4LL <= 0x7fffffffLL &&
+            (long long)a.B * a.H <= 0x7fffffffLL && getenv("RVDD_WARP_TMA")) {
+            CUtensorMap tm;
+            if (encode_map_2d(&tm, a.x, (unsigned long long)a.W * 4, (unsigned long long)a.B * a.H, (unsigned long long)a.W * 16,
+                              WH_BW * 4, WH_BH) == cudaSuccess) {
+                if (a.interp == 1)
+                    warp_hwc4_tma_kernel<1><<<grid, 256, 0, st>>>(a, tm);
+                else
+                    warp_hwc4_tma_kernel<0><<<grid, 256, 0, st>>>(a, tm);
+                return cudaGetLastError();
+            }
+        }
         if (a.interp == 1)
             warp_hwc4_kernel<1><<<grid, 256, 0, st>>>(a);
         else

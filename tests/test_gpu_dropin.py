@@ -194,23 +194,3 @@ def test_fused_two_iteration_variant_is_bit_exact(libpath, port):
             assert np.array_equal(flow[0].cpu().numpy(), ref), (h, w)
     finally:
         b.close()
-
-
-def test_per_level_cta_participation_is_bit_exact(libpath, port, monkeypatch):
-    """RVDD_PX_PER_CTA > 0: coarse pyramid levels are worked on by a subset of a group's CTAs (per-level barrier counters,
-    buffer parities handed over through the group's mailbox).  Slower than all-CTAs on B200 and therefore off by default,
-    but it must give the same bits."""
-    from rvdd_release_b200 import bridge as B
-    monkeypatch.setenv("RVDD_PX_PER_CTA", "1024")
-    b = B.Bridge(libpath)
-    try:
-        seq = synth.sequence(4, 180, 320, "iso3200").numpy().mean(axis=3, dtype=np.float32)
-        gray = torch.from_numpy(seq).cuda()
-        for src, tgt in (([0], [1]), ([0, 1, 2], [1, 2, 3])):
-            flow, iters = b.tvl1_flow(gray, src, tgt, trace=True, check=True)
-            for k, (s_, t_) in enumerate(zip(src, tgt)):
-                ref, it_ref, _, _, _ = port.tvl1flow_traced(seq[t_], seq[s_], err_mode=0)
-                assert np.array_equal(iters[k, :it_ref.shape[0]].cpu().numpy(), it_ref)
-                assert np.array_equal(flow[k].cpu().numpy(), ref)
-    finally:
-        b.close()

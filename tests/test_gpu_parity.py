@@ -419,3 +419,27 @@ def test_demosaic_argument_errors(bridge):
     with pytest.raises(BridgeError):
         bridge.remosaick_gray(torch.zeros(1, 3, 7, 8, device="cuda"))
     assert bridge.demosaic(torch.zeros(0, 4, 8, 8, device="cuda")).shape == (0, 3, 16, 16)
+
+
+@pytest.mark.parametrize("interp", ["bicubic", "bilinear"])
+def test_warp_hwc4_tma_staged_variant(bridge, monkeypatch, interp):
+    """RVDD_WARP_TMA=1: the (H, W, 4) warp with its tap box fetched by the TMA unit (measured slower than the L1 gathers and
+    therefore opt-in) against the oracle, including border tiles and a tile whose flow does not fit the box."""
+    monkeypatch.setenv("RVDD_WARP_TMA", "1")
+    B, H, W = 3, 75, 150
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, H, W, 4, generator=g)
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    f0 = torch.stack((2.5 + 1.5 * torch.sin(yy / 17.0), -1.5 + torch.cos(xx / 23.0)), 0)
+    f1 = torch.stack((-40.0 + 0.01 * xx, 25.0 + 0.02 * yy), 0)             # far outside on two sides
+    f2 = 6.0 * torch.randn(2, H, W, generator=g)                            # rough: boxes overflow -> direct gathers
+    flow = torch.stack((f0, f1, f2), 0)
+    xc = x.permute(0, 3, 1, 2)
+    ref, mref = warp_ref.warp(xc.contiguous(), flow, interp)
+    out = torch.empty(B, H, W, 4, device="cuda").permute(0, 3, 1, 2)
+    y, m = bridge.warp(xc.cuda(), flow.cuda(), interp, out=out)
+    assert rel_err(y.cpu().numpy(), ref.numpy()) <= WARP_RTOL
+    assert np.array_equal(m.cpu().numpy(), mref.numpy())
+    monkeypatch.delenv("RVDD_WARP_TMA")
+    y2, _ = bridge.warp(xc.cuda(), flow.cuda(), interp)
+    assert rel_err(y2.cpu().numpy(), ref.numpy()) <= WARP_RTOL

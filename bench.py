@@ -83,10 +83,10 @@ def hbm_peak():
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of one solver launch of this very workload (29 pairs), from the
-    committed `ncu --set full` capture (profiles/solver_kernel_r01.txt); None if the summary is missing."""
+    committed `ncu --set full` capture (profiles/solver_kernel_r02a.txt); None if the summary is missing."""
     try:
         tot = 0.0
-        for line in open(os.path.join(ROOT, "profiles", "solver_kernel_r01.txt")):
+        for line in open(os.path.join(ROOT, "profiles", "solver_kernel_r02a.txt")):
             f = line.split()
             if f and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 tot += float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
@@ -193,6 +193,8 @@ def run_ours(args, rank, local_rank, world):
     from rvdd_release_b200 import hostbind
     host_binding = hostbind.bind_to_gpu(local_rank) if not args.no_numa_bind else {"bound": False, "disabled": True}
     if world > 1:
+        # control plane only (the barrier and the max over ranks of two scalars per run): the data path has no collective,
+        # every rank works on its own sequence.  NCCL because the driver launches one rank per GPU over NCCL.
         dist.init_process_group("nccl", device_id=dev)
     br = B.default_bridge()
     if args.groups:
@@ -377,7 +379,7 @@ def run_ours(args, rank, local_rank, world):
     achieved = sb / (avg_solver_ms * 1e-3) / 1e9 if avg_solver_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "rvdd::solver_kernel (persistent TV-L1 solver, 1 launch per step)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
-                "traffic_source": "profiles/solver_kernel_r01.txt (ncu --set full of this workload, per launch)",
+                "traffic_source": "profiles/solver_kernel_r02a.txt (ncu --set full of this workload, per launch)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": sb, "avg_launch_ms": avg_solver_ms,
                 "share_of_step": avg_solver_ms * args.steps / ms if ms > 0 else None,
                 "step_algorithmic_bytes": step_bytes(sizes, iters),

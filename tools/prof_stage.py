@@ -14,6 +14,13 @@ if what.startswith("warp"):
     out = torch.empty_like(x)
     for _ in range(3):
         br.warp(x, flow, "bicubic", want_mask=False, out=out)
+elif what == "gauss":       # the pyramid kernels of a 29-pair batch (presmoothing + fused zoom-out levels)
+    import numpy as np
+    from rvdd_release_b200 import synth
+    frames = synth.sequence(30, 720, 1280, "iso3200", device="cuda")
+    gray = br.gray(frames)
+    for _ in range(2):
+        br.tvl1_flow(gray, np.arange(29), np.arange(1, 30))
 else:
     x = torch.rand(8, 4, 720, 1280, device="cuda") * 2 - 1
     for _ in range(3):

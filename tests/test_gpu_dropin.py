@@ -194,3 +194,39 @@ def test_fused_two_iteration_variant_is_bit_exact(libpath, port):
             assert np.array_equal(flow[0].cpu().numpy(), ref), (h, w)
     finally:
         b.close()
+
+
+def test_flow_edge_cases_and_errors(bridge, port):
+    """The reference's failure modes on this path kill the process (mask.c:229-232 abort when the Gaussian is wider than the
+    image, xmalloc.c:15-17 exit); the library reports them instead.  Plus: an empty batch, the smallest image the presmoothing
+    kernel accepts, a constant pair (normalisation with max == min copies, tvl1flow_lib.c:327-334) and bad pair indices."""
+    from rvdd_release_b200 import bridge as B
+    dev = "cuda"
+    # empty batch: nothing to do, empty result
+    g = torch.zeros(2, 32, 48, device=dev)
+    out = bridge.tvl1_flow(g, [], [])
+    assert tuple(out.shape) == (0, 2, 32, 48)
+    # smaller than the 9-tap presmoothing kernel: an error, not an abort
+    with pytest.raises(B.BridgeError):
+        bridge.tvl1_flow(torch.zeros(2, 4, 64, device=dev), [0], [1])
+    # pair index out of range
+    with pytest.raises(B.BridgeError):
+        bridge.tvl1_flow(g, [0], [2])
+    # a zoom factor so close to 1 that the reference would use more than 16 scales
+    p = B.TVL1Params()
+    bridge.lib.rvdd_default_params(ctypes.byref(p))
+    p.zfactor = 0.97
+    with pytest.raises(B.BridgeError):
+        bridge.tvl1_flow(torch.rand(2, 360, 640, device=dev), [0], [1], params=p)
+    # smallest sizes with more than one scale / exactly one scale, against the oracle
+    for h, w in ((17, 23), (12, 16), (9, 40)):
+        I0, I1 = synth.gray_pair(h, w, "iso3200")
+        ref, it_ref, _, _, _ = port.tvl1flow_traced(I0, I1, err_mode=0)
+        flow, iters = bridge.tvl1_flow(torch.from_numpy(np.stack([I0, I1])).cuda(), [1], [0], trace=True, check=True)
+        assert np.array_equal(iters[0, :it_ref.shape[0]].cpu().numpy(), it_ref), (h, w)
+        assert np.array_equal(flow[0].cpu().numpy(), ref), (h, w)
+    # constant images: den == 0 -> copied unnormalised, zero flow
+    c = np.full((40, 56), 7.0, np.float32)
+    ref = port.tvl1flow(c, c)
+    flow = bridge.tvl1_flow(torch.from_numpy(np.stack([c, c])).cuda(), [1], [0], check=True)
+    assert np.array_equal(flow[0].cpu().numpy(), ref) and np.count_nonzero(ref) == 0

@@ -32,9 +32,12 @@ __global__ void selftest_kernel(unsigned long long seed, int iters, unsigned lon
     unsigned long long state = seed + 0x1234567ULL * (blockIdx.x * blockDim.x + threadIdx.x);
     for (int it = 0; it < iters; it++) {
         const unsigned long long r1 = mix64(state++), r2 = mix64(state++), r3 = mix64(state++);
-        // ---- hypot: flow differences are small numbers; vary the exponent gap between the two operands
+        // ---- hypot: flow differences are small numbers; vary the exponent gap between the two operands, and visit the
+        // whole window the fast path accepts (2^-100 < max(|a|, |b|) < 2^40) including its edges
         const int mode = (int)(r3 & 7);
         float a = rnd_float(r1, -30, 8), b = rnd_float(r2, -30, 8);
+        if (mode == 5) a = rnd_float(r1, -104, -60), b = rnd_float(r2, -126, -60);
+        if (mode == 6) a = rnd_float(r1, 20, 41), b = rnd_float(r2, -10, 41);
         if (mode == 0) b = a * (1.0f + (float)((r3 >> 8) & 0xff) * 1.1920929e-07f);   // nearly equal
         if (mode == 1) b = 0.0f;
         if (mode == 2) a = rnd_float(r1, -3, 3), b = rnd_float(r2, -3, 3);
@@ -45,12 +48,14 @@ __global__ void selftest_kernel(unsigned long long seed, int iters, unsigned lon
         c[0]++;
         if (bad) c[1]++;
         else if (__float_as_uint(gf) != __float_as_uint(ge)) c[2]++;
-        // ---- division as used by the dual update (divisor >= 1) and by the thresholding step (any positive divisor)
-        const float num = (mode == 4) ? 0.0f : rnd_float(r2, -50, 20);
-        const float den = (mode & 1) ? (1.0f + fabsf(rnd_float(r1, -20, 12))) : fabsf(rnd_float(r1, -33, 30));
+        // ---- division as used by the dual update (divisor 1 + taut * g in [1, 2^41)) and by the thresholding step (divisor
+        // |grad|^2 in [1e-10, 2^21), or 1): accepted exactly when the callers accept it -- the numerator is 0 or at least 2^-60
+        // in magnitude (rvdd_num_key / RVDD_KEY_2M60) -- with numerators down to the threshold and a little below
+        const float num = (mode == 4) ? 0.0f : ((mode == 6) ? rnd_float(r2, -64, -56) : rnd_float(r2, -62, 24));
+        const float den = (mode & 1) ? (1.0f + fabsf(rnd_float(r1, -20, 40))) : fabsf(rnd_float(r1, -34, 20));
         const float q = rvdd_div_by_rcp(num, den, rvdd_rcp_refined(den));
         c[3]++;
-        if (!(den < RVDD_TWO_P40) || !rvdd_quot_ok(q, num)) c[4]++;
+        if (!(den < 2.199023255552e12f) || rvdd_num_key(num) < RVDD_KEY_2M60) c[4]++;          // den < 2^41
         else if (__float_as_uint(q) != __float_as_uint(__fdiv_rn(num, den))) c[5]++;
     }
     for (int k = 0; k < 6; k++) atomicAdd(&counters[k], c[k]);

@@ -224,15 +224,19 @@ __device__ __forceinline__ void tma_eval_row(TmaRing &T, int lane, const LaneEdg
     const float *s = T.stage(st) + ST_PAD + 4 * lane;
     RowIn<4> I;
     float4 v;
+    // The right neighbour column (index 4) is taken as staged even where no such column exists (last lane of the image row:
+    // it then holds the next row's first pixel); whatever is computed from it is never used (finish_row zeroes the forward
+    // difference on the last column).  Likewise the left neighbour of column 0 is the previous row's last column of p11 / p21,
+    // which is exactly zero (see eval_div, ZB), or the zero fill of the TMA unit above the first row.
 #define TAKE(o, dst)                                                \
     v = *reinterpret_cast<const float4 *>(s + (o));                 \
     I.dst[0] = v.x; I.dst[1] = v.y; I.dst[2] = v.z; I.dst[3] = v.w; \
-    I.dst[4] = E.right ? s[(o) + 4] : 0.f;
+    I.dst[4] = s[(o) + 4];
     TAKE(ST_OFF_P + 1 * ST_SLOT, p12) TAKE(ST_OFF_P + 3 * ST_SLOT, p22) TAKE(ST_OFF_P, a11) TAKE(ST_OFF_P + 2 * ST_SLOT, a21)
-    I.l11 = E.left ? 0.f : s[ST_OFF_P - 1];
-    I.l21 = E.left ? 0.f : s[ST_OFF_P + 2 * ST_SLOT - 1];
+    I.l11 = s[ST_OFF_P - 1];
+    I.l21 = s[ST_OFF_P + 2 * ST_SLOT - 1];
     float d1[5], d2[5];
-    eval_div<4>(I, E, first, last, up12, up22, R, d1, d2);
+    eval_div<4, true>(I, E, first, last, up12, up22, R, d1, d2);
     asm volatile("" ::: "memory");                  // keep the second half's shared-memory loads below this point
     TAKE(ST_OFF_U, u1) TAKE(ST_OFF_U + ST_SLOT, u2)
     TAKE(ST_OFF_C, gx) TAKE(ST_OFF_C + ST_SLOT, gy) TAKE(ST_OFF_C + 2 * ST_SLOT, rc)
@@ -366,12 +370,12 @@ __device__ __forceinline__ void f2_primal(const float (&u1)[4], const float (&u2
             d2[3] = rvdd_div_edge(-a21[2], b22[3], up22[3]);
         }
     }
-    bool bad = false;
+    unsigned tiny = 0xffffffffu;
 #pragma unroll
     for (int j = 0; j < 4; j++)
         rvdd_primal_px_fast(u1[j], u2[j], gx[j], gy[j], rvdd_grad2(gx[j], gy[j]), rc[j], d1[j], d2[j], K.l_t, K.theta, K.g0f, &n1[j],
-                            &n2[j], bad);
-    if (bad) {
+                            &n2[j], tiny);
+    if (tiny < RVDD_KEY_2M60) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const float2 n = rvdd_primal_px_slow(u1[j], u2[j], gx[j], gy[j], rvdd_grad2(gx[j], gy[j]), rc[j], d1[j], d2[j], K.l_t,
@@ -403,12 +407,13 @@ __device__ __forceinline__ void f2_dual(const float (&n1)[4], const float (&n2)[
         o11[j] = p11[j]; o12[j] = p12[j]; o21[j] = p21[j]; o22[j] = p22[j];
     }
     bool bad = false;
+    unsigned tiny = 0xffffffffu;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        rvdd_dual_px_fast(&o11[j], &o12[j], u1x[j], u1y[j], K.taut, bad);
-        rvdd_dual_px_fast(&o21[j], &o22[j], u2x[j], u2y[j], K.taut, bad);
+        rvdd_dual_px_fast(&o11[j], &o12[j], u1x[j], u1y[j], K.taut, bad, tiny);
+        rvdd_dual_px_fast(&o21[j], &o22[j], u2x[j], u2y[j], K.taut, bad, tiny);
     }
-    if (bad) {
+    if (bad || tiny < RVDD_KEY_2M60) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const float2 a = rvdd_dual_px_slow(p11[j], p12[j], u1x[j], u1y[j], K.taut);

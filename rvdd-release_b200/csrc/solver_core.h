@@ -145,7 +145,11 @@ template <int V> RVDD_HD void load_row_global(const IterPtrs &P, long long row, 
 // TH + primal update of one loaded row.  up12 / up22 hold p12 / p22 of the row above at the same V+1 columns
 // (zeros when y == 0).  first/last: y == 0 / y == ny-1.
 // Part 1 needs only the dual variable of the row (a11, a21, p12, p22, l11, l21): divergence of p.
-template <int V>
+// ZB ("zero border"): the caller relies on the invariant that the dual variable is EXACTLY zero where the divergence would
+// zero it -- p11 / p21 on the last column and p12 / p22 on the last row never leave their initial 0, because the forward
+// difference they are updated with is forced to 0 there (finish_row) and (0 + taut * 0) / ng = 0 -- so the selects that zero
+// those operands are skipped.  Only valid for rows read from the solver's own buffers (the staged path of solver.cu).
+template <int V, bool ZB = false>
 RVDD_HD void eval_div(const RowIn<V> &I, const LaneEdges &E, bool first, bool last, const float (&up12)[V + 1],
                       const float (&up22)[V + 1], RowState<V> &R, float (&d1)[V + 1], float (&d2)[V + 1])
 {
@@ -163,8 +167,8 @@ RVDD_HD void eval_div(const RowIn<V> &I, const LaneEdges &E, bool first, bool la
 #pragma unroll
     for (int j = 0; j <= V; j++) {
         const bool lastcol = (j == V - 1) ? E.last_own : ((j == V) ? E.last_nb : false);
-        const float a1 = lastcol ? 0.f : I.a11[j], a2 = lastcol ? 0.f : I.a21[j];
-        const float b1 = last ? 0.f : I.p12[j], b2 = last ? 0.f : I.p22[j];
+        const float a1 = (!ZB && lastcol) ? 0.f : I.a11[j], a2 = (!ZB && lastcol) ? 0.f : I.a21[j];
+        const float b1 = (!ZB && last) ? 0.f : I.p12[j], b2 = (!ZB && last) ? 0.f : I.p22[j];
         d1[j] = rvdd_div_inner(a1, j ? I.a11[j ? j - 1 : 0] : I.l11, b1, up12[j]);
         d2[j] = rvdd_div_inner(a2, j ? I.a21[j ? j - 1 : 0] : I.l21, b2, up22[j]);
     }
@@ -192,12 +196,12 @@ RVDD_HD void eval_primal(const RowIn<V> &I, const IterConsts &K, const float (&d
                          RowState<V> &R)
 {
 #if defined(__CUDA_ARCH__)
-    bool bad = false;
+    unsigned tiny = 0xffffffffu;
 #pragma unroll
     for (int j = 0; j <= V; j++)
         rvdd_primal_px_fast(I.u1[j], I.u2[j], I.gx[j], I.gy[j], rvdd_grad2(I.gx[j], I.gy[j]), I.rc[j], d1[j], d2[j], K.l_t, K.theta, K.g0f,
-                            &R.n1[j], &R.n2[j], bad);
-    if (bad) {      // rare: some quotient could not be proven exact -> the reference-exact routine for this row
+                            &R.n1[j], &R.n2[j], tiny);
+    if (tiny < RVDD_KEY_2M60) {      // rare: some quotient could not be proven exact -> the reference-exact routine for this row
 #pragma unroll
         for (int j = 0; j <= V; j++) {
             const float2 n = rvdd_primal_px_slow(I.u1[j], I.u2[j], I.gx[j], I.gy[j], rvdd_grad2(I.gx[j], I.gy[j]), I.rc[j], d1[j], d2[j],
@@ -256,12 +260,13 @@ RVDD_HD void finish_row(const IterPtrs &P, long long row, const LaneEdges &E, bo
     }
 #if defined(__CUDA_ARCH__)
     bool bad = false;
+    unsigned tiny = 0xffffffffu;
 #pragma unroll
     for (int j = 0; j < V; j++) {
-        rvdd_dual_px_fast(&o11[j], &o12[j], u1x[j], u1y[j], K.taut, bad);
-        rvdd_dual_px_fast(&o21[j], &o22[j], u2x[j], u2y[j], K.taut, bad);
+        rvdd_dual_px_fast(&o11[j], &o12[j], u1x[j], u1y[j], K.taut, bad, tiny);
+        rvdd_dual_px_fast(&o21[j], &o22[j], u2x[j], u2y[j], K.taut, bad, tiny);
     }
-    if (bad) {      // rare: recompute the row's dual update with the reference-exact routine
+    if (bad || tiny < RVDD_KEY_2M60) {      // rare: recompute the row's dual update with the reference-exact routine
 #pragma unroll
         for (int j = 0; j < V; j++) {
             const float2 a = rvdd_dual_px_slow(cur.p11[j], cur.p12[j], u1x[j], u1y[j], K.taut);

@@ -68,6 +68,13 @@ typedef struct rvdd_ctx rvdd_ctx;
 RVDD_API int rvdd_create(rvdd_ctx **out);
 RVDD_API int rvdd_destroy(rvdd_ctx *ctx);
 RVDD_API int rvdd_set_groups(rvdd_ctx *ctx, int n_groups);
+/* Which instantiation of the persistent solver a launch uses.  One iterates the primal-dual loop one pass per iteration; the
+ * other runs TWO iterations per pass on levels of at least `min_px` pixels (half the HBM traffic, a speculative exact stop
+ * with a one-iteration replay) and is faster when the inner loops run many iterations (noisy frames) and slower when they stop
+ * after one or two (clean frames).  Both return the same bits.  mode 0 = auto (decided per launch from the previous launch's
+ * iteration counts on this context; the default), 1 = never fuse, 2 = always.  min_px < 0 keeps the current threshold
+ * (default 600000).  Environment RVDD_FUSE=auto|0|1 sets the initial mode. */
+RVDD_API int rvdd_set_fuse(rvdd_ctx *ctx, int mode, int min_px);
 /* Watchdog of the persistent solver: a group barrier that waits longer than `ticks` SM clock cycles (default 4e9, about
  * 2 s; also settable with the environment variable RVDD_WATCHDOG_TICKS at context creation) makes the launch unwind.
  * Raise it under time-slicing / MPS / a debugger.  When it fires, every flow of that call is overwritten with NaN on

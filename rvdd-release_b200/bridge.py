@@ -35,6 +35,7 @@ _SIGNATURES = {
     "rvdd_destroy": (C.c_int, [C.c_void_p]),
     "rvdd_set_groups": (C.c_int, [C.c_void_p, C.c_int]),
     "rvdd_set_watchdog": (C.c_int, [C.c_void_p, C.c_longlong]),
+    "rvdd_set_fuse": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "rvdd_last_error": (C.c_char_p, []),
     "rvdd_abi_version": (C.c_int, []),
     "rvdd_gray_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -127,6 +128,11 @@ class Bridge:
 
     def set_groups(self, n):
         self._ck(self.lib.rvdd_set_groups(self.ctx, int(n)))
+
+    def set_fuse(self, mode="auto", min_px=-1):
+        """Solver instantiation: 'auto' (default), 'never' or 'always' run two iterations per pass on levels of at least
+        min_px pixels (rvdd_set_fuse).  Same bits either way."""
+        self._ck(self.lib.rvdd_set_fuse(self.ctx, {"auto": 0, "never": 1, "always": 2}[mode], int(min_px)))
 
     def set_watchdog(self, ticks):
         """Solver watchdog in SM clock ticks (default 4e9); a launch whose watchdog fires returns NaN flows."""

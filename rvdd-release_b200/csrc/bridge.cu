@@ -186,7 +186,13 @@ struct rvdd_ctx {
     cudaStream_t ws_stream = nullptr;
     bool ws_used = false;
     long long spin_limit = 4000000000LL;        // solver watchdog in clock64 ticks (~2 s at 2 GHz); rvdd_set_watchdog
-    int fuse_min_px = 0, fuse_first = 1;        // two-iterations-per-pass policy of the solver (RVDD_FUSE_MIN_PX / _FIRST)
+    // Two iterations per pass (solver.cu, iterate2_strip_tma).  fuse_mode: 0 = auto -- the solver instantiation with the fused
+    // pass is launched when the previous launch on this context averaged at least 4 inner iterations per warp on the finest
+    // level (noisy frames: ~19; clean frames: ~1.2, where the plain instantiation is faster) --, 1 = never, 2 = always.
+    // Levels with fewer than fuse_min_px pixels always iterate one at a time.  Both kernels produce the same bits.
+    int fuse_mode = 0, fuse_min_px = 600000, fuse_first = 0;
+    int *stat_host = nullptr;                   // pinned + mapped: 16 x (finest-level iterations per pair and warp) of the last launch
+    int *stat_dev = nullptr;                    // its device alias
 };
 
 static int create_resources(rvdd_ctx *c)
@@ -210,8 +216,12 @@ static int create_resources(rvdd_ctx *c)
         const long long v = atoll(env);
         if (v > 0) c->spin_limit = v;
     }
+    if (const char *env = getenv("RVDD_FUSE")) c->fuse_mode = (env[0] == 'a') ? 0 : (atoi(env) ? 2 : 1);   // auto | 0 | 1
     if (const char *env = getenv("RVDD_FUSE_MIN_PX")) c->fuse_min_px = atoi(env);     // tuning / A-B runs only
     if (const char *env = getenv("RVDD_FUSE_FIRST")) c->fuse_first = atoi(env);
+    CK(cudaHostAlloc((void **)&c->stat_host, sizeof(int), cudaHostAllocMapped));
+    *c->stat_host = 0;
+    CK(cudaHostGetDevicePointer((void **)&c->stat_dev, c->stat_host, 0));
     CK(cudaStreamCreateWithFlags(&c->st_compute, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking));
@@ -258,6 +268,7 @@ extern "C" int rvdd_destroy(rvdd_ctx *c)
         if (c->ring_ev[i]) cudaEventDestroy(c->ring_ev[i]);
     }
     if (c->ws_ev) cudaEventDestroy(c->ws_ev);
+    if (c->stat_host) cudaFreeHost(c->stat_host);
     for (cudaEvent_t ev : c->events) cudaEventDestroy(ev);
     for (cudaEvent_t ev : c->prof_ev) cudaEventDestroy(ev);
     if (c->st_compute) cudaStreamDestroy(c->st_compute);
@@ -274,6 +285,15 @@ extern "C" int rvdd_set_groups(rvdd_ctx *c, int n)
     return 0;
 }
 
+extern "C" int rvdd_set_fuse(rvdd_ctx *c, int mode, int min_px)
+{
+    if (!c) return fail("rvdd_set_fuse: null context");
+    if (mode < 0 || mode > 2) return fail("rvdd_set_fuse: mode must be 0 (auto), 1 (never) or 2 (always)");
+    c->fuse_mode = mode;
+    if (min_px >= 0) c->fuse_min_px = min_px;
+    return 0;
+}
+
 extern "C" int rvdd_set_watchdog(rvdd_ctx *c, long long ticks)
 {
     if (!c) return fail("rvdd_set_watchdog: null context");
@@ -285,8 +305,11 @@ extern "C" int rvdd_set_watchdog(rvdd_ctx *c, long long ticks)
 // A solver launch whose watchdog fired unwinds early and leaves the flow buffer partly written: make that visible without
 // a host synchronisation by overwriting the whole result with NaN (every consumer then fails loudly instead of using
 // stale values).  One tiny launch per solver call; the threads of a healthy launch read one word and return.
-__global__ void poison_on_failure_kernel(const int *__restrict__ status, float *__restrict__ flow, long long n)
+__global__ void poison_on_failure_kernel(const int *__restrict__ status, float *__restrict__ flow, long long n, int *stat_host,
+                                         int stat_den)
 {
+    // (also: the launch's finest-level iteration average, x16, goes to the host's mapped word for the next launch's kernel choice)
+    if (blockIdx.x == 0 && threadIdx.x == 0) *stat_host = (int)(((long long)status[1] * 16) / stat_den);
     if (*status == 0) return;
     const float nan = __int_as_float(0x7fc00000);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) flow[i] = nan;
@@ -481,12 +504,13 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
         }
         CK(cudaEventRecord(c->prof_ev[2 * c->prof_n], st));
     }
-    CK(launch_solver(A, st));
+    const bool fused_kernel = c->fuse_mode == 2 || (c->fuse_mode == 0 && *(volatile int *)c->stat_host >= 4 * 16);
+    CK(launch_solver(A, fused_kernel, st));
     if (c->prof) {
         CK(cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st));
         c->prof_n++;
     }
-    poison_on_failure_kernel<<<c->sms, 256, 0, st>>>(status, flow, (long long)K * 2 * nx * ny);
+    poison_on_failure_kernel<<<c->sms, 256, 0, st>>>(status, flow, (long long)K * 2 * nx * ny, c->stat_dev, K * p.nwarps);
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->ws_ev, st));
     c->ws_stream = st;

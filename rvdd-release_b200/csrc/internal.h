@@ -44,7 +44,7 @@ struct SolverArgs {
     unsigned *bar;                      // [ngroups * 32] (one counter per 128 B)
     double *partials;                   // [ngroups][2 slots][2 sums][ctas_per_group]
     unsigned long long *scale_ns;       // optional [npairs][RVDD_MAX_SCALES + 1] globaltimer stamps (profiling)
-    int *status;                        // [0]: watchdog flag
+    int *status;                        // [0]: watchdog flag, [1]: finest-level inner iterations of the launch (summed over pairs)
     int ngroups, ctas_per_group;
     long long spin_limit;               // watchdog, in clock64 ticks
     int fuse_min_px;                    // levels with at least this many pixels (and nx % 4 == 0) run two iterations per pass
@@ -71,7 +71,7 @@ cudaError_t launch_gray(const float *img, float *gray, long long npix_total, int
 
 // solver.cu
 cudaError_t solver_max_ctas(int *ctas_per_sm, int *sms);
-cudaError_t launch_solver(const SolverArgs &args, cudaStream_t st);
+cudaError_t launch_solver(const SolverArgs &args, bool fused_kernel, cudaStream_t st);
 int solver_threads();
 
 // warp.cu

@@ -24,7 +24,7 @@ __global__ void setup_kernel(int *slots, int npairs, unsigned *bar, int nbar, in
         slots[2 * i + 1] = (int)0x80000000;      // running max
     }
     if (i < nbar) bar[i] = 0u;
-    if (i == 0) status[0] = 0;
+    if (i == 0) { status[0] = 0; status[1] = 0; }
 }
 
 cudaError_t launch_setup(int *slots, int npairs, unsigned *bar, int nbar, int *status, cudaStream_t st)

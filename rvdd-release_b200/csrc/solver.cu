@@ -121,30 +121,21 @@ __device__ __forceinline__ double group_sum(const GroupCtx &g, int slot, double 
 #define ST_OFF_U 416
 #define ST_OFF_P 704
 #define ST_ROW 1248                      // floats per stage (4992 B, a multiple of 128 B)
-// RVDD_FUSE2 compiles the two-iterations-per-pass path in (iterate2_strip_tma below).  It is OFF in the shipped library:
-// measured on B200 (29 pairs 1280x720, profiles/solver_fused2_r02.txt) the fused pass halves the DRAM traffic (112 vs 191
-// GB) but the kernel is bound by dependent-issue latency at 12 warps per SM, not by HBM -- 48.6 ms against 42.1 ms --
-// and merely compiling both loops into one kernel costs the single-iteration loop 15 % (register allocation).
-#ifndef ST_STAGES
-#ifdef RVDD_FUSE2
-#define ST_STAGES 3                      // the fused pass keeps rows L-1 and L while row L+1 is in flight
-#else
-#define ST_STAGES 2
-#endif
-#endif
-#define ST_WARP_BYTES (ST_STAGES * ST_ROW * 4 + 128)  // + the mbarriers; keeps every warp's stages 128-byte aligned
+// Ring depth NST (a template parameter of everything below): 2 rows in flight for the single-iteration pass; the pass that
+// fuses two iterations keeps rows L-1 and L while row L+1 is in flight and uses 3.
+#define ST_WARP_BYTES(NST) ((NST) * ST_ROW * 4 + 128)  // + the mbarriers; keeps every warp's stages 128-byte aligned
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-// Per-warp ring of ST_STAGES staged rows.  Rows are issued and consumed strictly in order, so two running counters say
-// everything: row number n lives in stage n % ST_STAGES and completes that stage's mbarrier phase (n / ST_STAGES) & 1.
-struct TmaRing {
-    unsigned char *base;                 // stage k at base + k * ST_ROW * 4, mbarrier k at base + ST_STAGES * ST_ROW * 4 + 16 k
+// Per-warp ring of NST staged rows.  Rows are issued and consumed strictly in order, so two running counters say
+// everything: row number n lives in stage n % NST and completes that stage's mbarrier phase (n / NST) & 1.
+template <int NST> struct TmaRing {
+    unsigned char *base;                 // stage k at base + k * ST_ROW * 4, mbarrier k at base + NST * ST_ROW * 4 + 16 k
     unsigned issued, taken;
     __device__ __forceinline__ float *stage(unsigned k) const { return reinterpret_cast<float *>(base + (size_t)k * ST_ROW * 4); }
     __device__ __forceinline__ unsigned long long *bar(unsigned k) const
     {
-        return reinterpret_cast<unsigned long long *>(base + (size_t)ST_STAGES * ST_ROW * 4 + 16 * k);
+        return reinterpret_cast<unsigned long long *>(base + (size_t)NST * ST_ROW * 4 + 16 * k);
     }
 };
 
@@ -193,10 +184,11 @@ __device__ __forceinline__ void tma_box(const CUtensorMap *tm, float *dst, int c
 // elected lane: queue the three box copies of the image row `delta` floats below the strip's first row into `stage`.
 // Out-of-range coordinates (left of pixel 0 of the plane, beyond its end) are zero-filled by the TMA unit and still
 // count towards the transaction bytes, so the byte count is a constant.
-__device__ __forceinline__ void tma_issue_row(const SolverArgs &A, const TmaSrc &Q, int delta, const TmaRing &T, unsigned n)
+template <int NST>
+__device__ __forceinline__ void tma_issue_row(const SolverArgs &A, const TmaSrc &Q, int delta, const TmaRing<NST> &T, unsigned n)
 {
-    float *stage = T.stage(n % ST_STAGES);
-    unsigned long long *bar = T.bar(n % ST_STAGES);
+    float *stage = T.stage(n % NST);
+    unsigned long long *bar = T.bar(n % NST);
     mbar_expect_tx(bar, 9u * ST_SLOT * 4u);
     tma_box(&A.tm3, stage + ST_OFF_C, Q.c0 + delta, Q.row_c, bar);
     tma_box(&A.tm2, stage + ST_OFF_U, Q.c0 + delta, Q.row_u, bar);
@@ -206,11 +198,12 @@ __device__ __forceinline__ void tma_issue_row(const SolverArgs &A, const TmaSrc 
 // all lanes: wait for stage `st`, then evaluate the staged row straight out of shared memory.  The row is consumed in
 // two halves (dual variable -> divergence, then flow + constants -> primal update) so that at most half of its 47
 // input values are live in registers at any time.
-__device__ __forceinline__ void tma_eval_row(TmaRing &T, int lane, const LaneEdges &E, bool first, bool last,
+template <int NST>
+__device__ __forceinline__ void tma_eval_row(TmaRing<NST> &T, int lane, const LaneEdges &E, bool first, bool last,
                                              const IterConsts &K, const float (&up12)[5], const float (&up22)[5],
                                              RowState<4> &R, int *status)
 {
-    const unsigned st = T.taken % ST_STAGES, parity = (T.taken / ST_STAGES) & 1u;
+    const unsigned st = T.taken % NST, parity = (T.taken / NST) & 1u;
     T.taken++;
     unsigned long long *bar = T.bar(st);
     bool ok = mbar_try_wait(bar, parity);
@@ -245,7 +238,8 @@ __device__ __forceinline__ void tma_eval_row(TmaRing &T, int lane, const LaneEdg
 }
 
 // One warp's strip with staged rows (V = 4): same arithmetic as iterate_strip<4>, different data path.
-__device__ __forceinline__ double iterate_strip_tma(const SolverArgs &SA, int group, const IterPtrs &P, TmaRing &T, int lane,
+template <int NST>
+__device__ __forceinline__ double iterate_strip_tma(const SolverArgs &SA, int group, const IterPtrs &P, TmaRing<NST> &T, int lane,
                                                     int warp_x0, int y0, int y1, int nx, int ny, const IterConsts &K,
                                                     int *status)
 {
@@ -261,16 +255,16 @@ __device__ __forceinline__ double iterate_strip_tma(const SolverArgs &SA, int gr
     Q.row_p = group * RVDD_NPLANES + RVDD_PL_P + 4 * P.pc;
     double err = 0.0;
 
-    // prologue: the first ST_STAGES rows of the strip go in flight at once
+    // prologue: the first NST rows of the strip go in flight at once
     __syncwarp();
     const unsigned n0 = T.issued;                        // == T.taken: the ring is empty between strips
     if (elect_one()) {
         fence_proxy_async();                             // other CTAs' stores (generic proxy) -> our bulk reads
 #pragma unroll
-        for (int k = 0; k < ST_STAGES; k++)
+        for (int k = 0; k < NST; k++)
             if (k < nr) tma_issue_row(SA, Q, k * nx, T, n0 + k);
     }
-    T.issued = n0 + (unsigned)min(nr, ST_STAGES);
+    T.issued = n0 + (unsigned)min(nr, NST);
     float up12[5], up22[5];
     long long row = (long long)y0 * nx + x0;
     if (active) {
@@ -280,11 +274,11 @@ __device__ __forceinline__ double iterate_strip_tma(const SolverArgs &SA, int gr
         for (int j = 0; j < 5; j++) up12[j] = up22[j] = 0.f;
     }
 
-    // after a row has been consumed its stage is refilled with the row ST_STAGES further down
+    // after a row has been consumed its stage is refilled with the row NST further down
     auto refill = [&](int consumed) {
         __syncwarp();                                    // every lane has pulled its values out of the stage
-        if (consumed + ST_STAGES < nr) {
-            if (elect_one()) tma_issue_row(SA, Q, (consumed + ST_STAGES) * nx, T, T.issued);
+        if (consumed + NST < nr) {
+            if (elect_one()) tma_issue_row(SA, Q, (consumed + NST) * nx, T, T.issued);
             T.issued++;
         }
     };
@@ -439,7 +433,8 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 }
 
 // One warp's strip of the fused pass: columns [c0, c0 + 128) (lanes 1..30 own c0 + 4 .. c0 + 123), output rows [y0, y1).
-__device__ __forceinline__ void iterate2_strip_tma(const SolverArgs &SA, int group, const IterPtrs &P, TmaRing &T, int lane, int c0,
+template <int NST>
+__device__ __forceinline__ void iterate2_strip_tma(const SolverArgs &SA, int group, const IterPtrs &P, TmaRing<NST> &T, int lane, int c0,
                                                    int y0, int y1, int nx, int ny, const IterConsts &K, int *status, double &errA,
                                                    double &errB)
 {
@@ -462,12 +457,14 @@ __device__ __forceinline__ void iterate2_strip_tma(const SolverArgs &SA, int gro
     if (elect_one()) {
         fence_proxy_async();                             // other CTAs' stores (generic proxy) -> our bulk reads
 #pragma unroll
-        for (int k = 0; k < ST_STAGES; k++)
+        for (int k = 0; k < NST; k++)
             if (k < nrows) tma_issue_row(SA, Q, k * nx, T, n0 + k);
     }
-    T.issued = n0 + (unsigned)min(nrows, ST_STAGES);
+    T.issued = n0 + (unsigned)min(nrows, NST);
 
-    // carried between rows: u^A of the last staged row, p^A and u^B of the row before it
+    // carried between rows: u^A of the last staged row, p^A and u^B of the row before it.  The pipeline fills and drains
+    // by simply running every stage in every step: what a stage computes before its inputs exist (zeros at first, then
+    // finite values of neighbouring rows) is neither stored nor accumulated and never reaches a stage whose output counts.
     float uA1[4], uA2[4], pA11[4], pA12[4], pA21[4], pA22[4], uB1[4], uB2[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) uA1[j] = uA2[j] = pA11[j] = pA12[j] = pA21[j] = pA22[j] = uB1[j] = uB2[j] = 0.f;
@@ -477,22 +474,20 @@ __device__ __forceinline__ void iterate2_strip_tma(const SolverArgs &SA, int gro
     for (int L = R0; L <= y1 + 1; ++L) {
         const bool haveL = (L <= R1);
         const unsigned iL = n0 + (unsigned)(L - R0);
-        const float *sL = T.stage(iL % ST_STAGES) + ST_PAD + 4 * lane;                       // row L
-        const float *sM = T.stage((iL + ST_STAGES - 1) % ST_STAGES) + ST_PAD + 4 * lane;     // row L - 1
-        if (haveL) mbar_wait(T.bar(iL % ST_STAGES), (iL / ST_STAGES) & 1u, status);
+        const float *sL = T.stage(iL % NST) + ST_PAD + 4 * lane;                       // row L
+        const float *sM = T.stage((iL + NST - 1) % NST) + ST_PAD + 4 * lane;     // row L - 1
+        if (haveL) mbar_wait(T.bar(iL % NST), (iL / NST) & 1u, status);
+        const int r = L - 1, q = L - 2;
 
-        // ---- S1: primal A of row L
+        // ---- S1: primal A of row L (a row below the image recomputes the stage's stale contents: unused, `down` is false)
         float nA1[4], nA2[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) nA1[j] = nA2[j] = 0.f;
-        if (haveL && L >= Lstart) {
+        {
             float u1[4], u2[4], gx[4], gy[4], rc[4], a11[4], a21[4], b12[4], b22[4], up12[4], up22[4], res[4];
             ld4s(sL + ST_OFF_P, a11); ld4s(sL + ST_OFF_P + 2 * ST_SLOT, a21);
             ld4s(sL + ST_OFF_P + ST_SLOT, b12); ld4s(sL + ST_OFF_P + 3 * ST_SLOT, b22);
-            const float l11 = E.left ? 0.f : sL[ST_OFF_P - 1], l21 = E.left ? 0.f : sL[ST_OFF_P + 2 * ST_SLOT - 1];
-            if (L > 0) {
-                ld4s(sM + ST_OFF_P + ST_SLOT, up12); ld4s(sM + ST_OFF_P + 3 * ST_SLOT, up22);
-            } else {
+            const float l11 = sL[ST_OFF_P - 1], l21 = sL[ST_OFF_P + 2 * ST_SLOT - 1];       // column -1: exactly zero (ZB)
+            ld4s(sM + ST_OFF_P + ST_SLOT, up12); ld4s(sM + ST_OFF_P + 3 * ST_SLOT, up22);
+            if (L == 0) {
 #pragma unroll
                 for (int j = 0; j < 4; j++) up12[j] = up22[j] = 0.f;
             }
@@ -506,12 +501,8 @@ __device__ __forceinline__ void iterate2_strip_tma(const SolverArgs &SA, int gro
         }
 
         // ---- S2: dual A of row L - 1 (its forward differences need u^A of rows L - 1 and L)
-        const int r = L - 1;
-        const bool s2 = (r >= Lstart) && (r <= ny - 1);
         float qA11[4], qA12[4], qA21[4], qA22[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) qA11[j] = qA12[j] = qA21[j] = qA22[j] = 0.f;
-        if (s2) {
+        {
             ld4s(sM + ST_OFF_P, qA11); ld4s(sM + ST_OFF_P + ST_SLOT, qA12);
             ld4s(sM + ST_OFF_P + 2 * ST_SLOT, qA21); ld4s(sM + ST_OFF_P + 3 * ST_SLOT, qA22);
             const float r1 = __shfl_down_sync(0xffffffffu, uA1[0], 1), r2 = __shfl_down_sync(0xffffffffu, uA2[0], 1);
@@ -519,30 +510,28 @@ __device__ __forceinline__ void iterate2_strip_tma(const SolverArgs &SA, int gro
         }
 
         // ---- S3: primal B of row L - 1
-        const bool s3 = s2 && (r >= y0);
         float nB1[4], nB2[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) nB1[j] = nB2[j] = 0.f;
-        if (s3) {
+        {
             float gx[4], gy[4], rc[4], up12[4], up22[4], res[4];
             ld4s(sM + ST_OFF_C, gx); ld4s(sM + ST_OFF_C + ST_SLOT, gy); ld4s(sM + ST_OFF_C + 2 * ST_SLOT, rc);
+            // left neighbours of p^A: lane - 1's last pixel; on column 0 that is lane 0's own (shfl_up) or a halo lane's value,
+            // and must read as the zero the reference's divergence uses there
             const float t11 = __shfl_up_sync(0xffffffffu, qA11[3], 1), t21 = __shfl_up_sync(0xffffffffu, qA21[3], 1);
             const float l11 = E.left ? 0.f : t11, l21 = E.left ? 0.f : t21;
 #pragma unroll
             for (int j = 0; j < 4; j++) { up12[j] = r > 0 ? pA12[j] : 0.f; up22[j] = r > 0 ? pA22[j] : 0.f; }
             f2_primal(uA1, uA2, gx, gy, rc, qA11, qA21, qA12, qA22, l11, l21, up12, up22, r == 0, r == ny - 1, E, K, nB1, nB2, res);
-            if (owner && r < y1) {
+            if (owner && r >= y0 && r < y1) {
 #pragma unroll
                 for (int j = 0; j < 4; j++) errB += (double)res[j];
             }
         }
 
         // ---- S4: dual B of row L - 2, stores
-        const int q = L - 2;
-        if (q >= y0 && q < y1) {
+        {
             const float r1 = __shfl_down_sync(0xffffffffu, uB1[0], 1), r2 = __shfl_down_sync(0xffffffffu, uB2[0], 1);
             f2_dual(uB1, uB2, r1, r2, nB1, nB2, q + 1 <= ny - 1, E, K, pA11, pA12, pA21, pA22);
-            if (owner) {
+            if (owner && q >= y0 && q < y1) {
                 const long long o = (long long)q * nx + colq;
                 Vec<4>::st(P.nu1() + o, uB1);
                 Vec<4>::st(P.nu2() + o, uB2);
@@ -571,29 +560,34 @@ __device__ __forceinline__ void iterate2_strip_tma(const SolverArgs &SA, int gro
     T.taken = T.issued;
 }
 
-// strip plan of the fused pass: column segments of F2_OUT pixels, the first one starting one (halo) lane left of column 0
-__device__ __forceinline__ void iterate2_group(const SolverArgs &A, int group, const IterPtrs &P, TmaRing &T, int nx, int ny,
+// Work split of the fused pass: column segments of F2_OUT pixels (the first one starting one halo lane left of column 0), and
+// the ncol * ny segment-rows, taken column after column, dealt out evenly -- every warp gets the same number of rows, in one
+// strip or, where its share crosses from one column segment into the next, in two (1280 x 720 on 60 warps: 11 segments x 720
+// rows = 132 rows each, instead of 5 strips of 144 rows per segment with 5 of the 60 warps idle).
+template <int NST>
+__device__ __forceinline__ void iterate2_group(const SolverArgs &A, int group, const IterPtrs &P, TmaRing<NST> &T, int nx, int ny,
                                                const IterConsts &K, int gwarp, int nwarps_group, int *status, double &errA,
                                                double &errB)
 {
     const int lane = threadIdx.x & 31;
     const int ncol = (nx + F2_OUT - 1) / F2_OUT;
-    int per_col = nwarps_group / ncol;
-    if (per_col < 1) per_col = 1;
-    int rows = (ny + per_col - 1) / per_col;
-    if (rows < 1) rows = 1;
-    const int nstrips = (ny + rows - 1) / rows, total = ncol * nstrips;
-    for (int w = gwarp; w < total; w += nwarps_group) {
-        const int col = w % ncol, strip = w / ncol;
-        const int y0 = strip * rows, y1 = min(ny, y0 + rows);
+    const int total = ncol * ny;
+    int share = (total + nwarps_group - 1) / nwarps_group;
+    if (share < 4) share = 4;                            // tiny levels: a strip of fewer rows is all halo
+    int pos = gwarp * share;
+    const int end = min(total, pos + share);
+    while (pos < end) {
+        const int col = pos / ny, y0 = pos - col * ny;
+        const int y1 = min(ny, y0 + (end - pos));
         iterate2_strip_tma(A, group, P, T, lane, col * F2_OUT - 4, y0, y1, nx, ny, K, status, errA, errB);
+        pos += y1 - y0;
     }
 }
 
 // Distribute the image over the group's warps: column segments of 32*V pixels, strips of `rows` rows
 // (iterate_strip, the direct-load version, is in solver_core.h and shared with the host-compiled unit tests).
-template <int V>
-__device__ __forceinline__ double iterate_group(const SolverArgs &A, int group, const IterPtrs &P, TmaRing &T, int nx, int ny,
+template <int V, int NST>
+__device__ __forceinline__ double iterate_group(const SolverArgs &A, int group, const IterPtrs &P, TmaRing<NST> &T, int nx, int ny,
                                                 const IterConsts &K, int gwarp, int nwarps_group, int *status)
 {
     const int lane = threadIdx.x & 31;
@@ -670,20 +664,25 @@ __device__ __forceinline__ void warp_consts_group(const float *I0, const float *
 
 // ------------------------------------------------------------------------------------------------ the kernel
 
+// F2: the instantiation whose big levels may run two iterations per pass (iterate2_strip_tma).  It is a separate kernel, not
+// a flag: compiled into one function, the two row loops cost each other 15-20 % (register allocation), and the host picks the
+// instantiation per launch (bridge.cu: by the iteration counts of the previous launch).  Both give the same bits.
+template <bool F2>
 __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel(const __grid_constant__ SolverArgs A)
 {
+    constexpr int NST = F2 ? 3 : 2;
     __shared__ double s_red[SOLVER_WARPS], s_red2[SOLVER_WARPS];
     __shared__ double s_val, s_val2;
     __shared__ int s_flag;
     extern __shared__ __align__(128) unsigned char s_dyn[];
 
     // per-warp staging ring for the bulk-copy row pipeline
-    TmaRing T;
+    TmaRing<NST> T;
     {
-        T.base = s_dyn + (size_t)(threadIdx.x >> 5) * ST_WARP_BYTES;
+        T.base = s_dyn + (size_t)(threadIdx.x >> 5) * ST_WARP_BYTES(NST);
         T.issued = T.taken = 0u;
 #pragma unroll
-        for (int k = 0; k < ST_STAGES; k++)
+        for (int k = 0; k < NST; k++)
             if ((threadIdx.x & 31) == 0) mbar_init(T.bar(k), 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncthreads();
@@ -755,6 +754,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
                 if (!group_sync(g, &s_flag)) return;
 
                 unsigned long long ns_consts = 0ULL, ns_iter = 0ULL;
+                int prev_iters = 0;                      // iterations of this level's previous warp (fused-pass policy)
                 for (int w = 0; w < A.nwarps; w++) {
                     const unsigned long long tp0 = stamping ? now_ns() : 0ULL;
                     // ---- warp constants (:143-159): bicubic samples of I1, I1x, I1y at x + u
@@ -768,22 +768,22 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
                     // come back, and if the first of the two already met the stopping rule that iteration is replayed
                     // alone from the input buffers, which the fused pass leaves untouched.
                     int it = 0;
-                    float err = INFINITY;
-#if defined(RVDD_FUSE2)
-                    const bool can_fuse = ((nx & 3) == 0) && n >= A.fuse_min_px;
-#else
-                    const bool can_fuse = false;
-#endif
+                    float err = INFINITY, err_before = INFINITY;
+                    const bool can_fuse = F2 && ((nx & 3) == 0) && n >= A.fuse_min_px;
                     while (err > A.eps2 && it < RVDD_MAX_ITERATIONS) {
                         IterPtrs P;
                         P.S = S; P.PL = PL; P.uc = uc; P.pc = pc;
-                        const bool fused = can_fuse && it >= A.fuse_first && it + 2 <= RVDD_MAX_ITERATIONS;
+                        // Two iterations in one pass only when the loop is not expected to stop after the first of them (a
+                        // stop there costs the pass plus a replay): at the start of a loop, if the previous warp of this
+                        // level needed at least three iterations; later, if the residual extrapolated with its last decay
+                        // ratio stays above eps^2 for one more iteration.  Efficiency only -- every CTA takes the same decision
+                        // from the same numbers, and the iteration the loop stops at does not depend on it.
+                        bool fused = can_fuse && it >= A.fuse_first && it + 2 <= RVDD_MAX_ITERATIONS;
+                        if (fused) fused = (it == 0) ? (prev_iters >= 3) : (err * (err / err_before) > A.eps2);
                         double e = 0.0, e2 = 0.0;
-#if defined(RVDD_FUSE2)
-                        if (fused)
+                        if (F2 && fused)
                             iterate2_group(A, group, P, T, nx, ny, K, gwarp, gwarps, A.status, e, e2);
                         else
-#endif
                             e = ((nx & 3) == 0) ? iterate_group<4>(A, group, P, T, nx, ny, K, gwarp, gwarps, A.status)
                                                 : iterate_group<1>(A, group, P, T, nx, ny, K, gwarp, gwarps, A.status);
                         // CTA partials in a fixed order, then the group reduction rides on the barrier
@@ -803,11 +803,13 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
                         const double tot = group_sum(g, 2 * g.slot, &s_val);
                         const double tot2 = fused ? group_sum(g, 2 * g.slot + 1, &s_val2) : 0.0;
                         g.slot ^= 1;
+                        err_before = err;
                         err = FDIV((float)tot, (float)n);        // error /= size (:223)
                         if (!fused) {
                             it++;
                         } else if (err > A.eps2) {               // the loop continues past iteration A: B is the state
                             it += 2;
+                            err_before = err;
                             err = FDIV((float)tot2, (float)n);
                         } else {                                 // the reference stops after iteration A: replay it alone
                             iterate_group<4>(A, group, P, T, nx, ny, K, gwarp, gwarps, A.status);
@@ -817,10 +819,12 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
                         uc ^= 1;
                         pc ^= 1;
                     }
+                    prev_iters = it;
                     if (g.cta == 0 && threadIdx.x == 0) {
                         const long long t = ((long long)pair * RVDD_MAX_SCALES + s) * A.nwarps + w;
                         if (A.iters_out) A.iters_out[t] = it;
                         if (A.err_out) A.err_out[t] = err;
+                        if (s == 0) atomicAdd(A.status + 1, it);     // finest-level iterations of the launch (kernel choice)
                     }
                     if (stamping) {
                         const unsigned long long tp2 = now_ns();
@@ -886,17 +890,27 @@ cudaError_t solver_max_ctas(int *ctas_per_sm, int *sms)
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(solver_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVER_WARPS * ST_WARP_BYTES);
+    // both instantiations must fit the same grid (they share the workspace layout): take the smaller occupancy
+    int occ1 = 0, occ2 = 0;
+    e = cudaFuncSetAttribute(solver_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVER_WARPS * ST_WARP_BYTES(2));
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, solver_kernel, SOLVER_THREADS,
-                                                         SOLVER_WARPS * ST_WARP_BYTES);
+    e = cudaFuncSetAttribute(solver_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVER_WARPS * ST_WARP_BYTES(3));
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, solver_kernel<false>, SOLVER_THREADS, SOLVER_WARPS * ST_WARP_BYTES(2));
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, solver_kernel<true>, SOLVER_THREADS, SOLVER_WARPS * ST_WARP_BYTES(3));
+    if (e != cudaSuccess) return e;
+    *ctas_per_sm = occ1 < occ2 ? occ1 : occ2;
+    return cudaSuccess;
 }
 
-cudaError_t launch_solver(const SolverArgs &args, cudaStream_t st)
+cudaError_t launch_solver(const SolverArgs &args, bool fused_kernel, cudaStream_t st)
 {
     void *params[] = {(void *)&args};
     const dim3 grid(args.ngroups * args.ctas_per_group), block(SOLVER_THREADS);
-    return cudaLaunchCooperativeKernel((const void *)solver_kernel, grid, block, params, SOLVER_WARPS * ST_WARP_BYTES, st);
+    if (fused_kernel)
+        return cudaLaunchCooperativeKernel((const void *)solver_kernel<true>, grid, block, params, SOLVER_WARPS * ST_WARP_BYTES(3), st);
+    return cudaLaunchCooperativeKernel((const void *)solver_kernel<false>, grid, block, params, SOLVER_WARPS * ST_WARP_BYTES(2), st);
 }
 
 }  // namespace rvdd

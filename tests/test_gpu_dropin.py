@@ -175,23 +175,26 @@ def test_watchdog_poisons_the_result(bridge):
         b.close()
 
 
-def test_fused_two_iteration_variant_is_bit_exact(libpath, port):
-    """The -DRVDD_FUSE2 build (two primal-dual iterations per pass with a speculative exact stop and a one-iteration
-    replay; measured slower than the shipped pass and therefore off by default) must still give the
-    reference's bits and iteration counts."""
+def test_both_solver_instantiations_are_bit_exact(libpath, port):
+    """The solver exists twice: one iteration per pass, and two iterations per pass on big levels (speculative exact stop with a
+    one-iteration replay).  The library picks per launch ('auto': from the previous launch's iteration counts); forced either
+    way, and with the fused pass on EVERY level (min_px = 0: tiny strips, odd pyramids), the reference's bits and iteration
+    counts must come out."""
     from rvdd_release_b200 import bridge as B
-    variant = os.path.join(os.path.dirname(libpath), "libBridge_fuse2.so")
-    if not os.path.exists(variant):
-        pytest.skip("variant library not built")
-    b = B.Bridge(variant)
+    b = B.Bridge(libpath)
     try:
-        for h, w, iso in ((180, 320, "iso3200"), (97, 132, "iso12800"), (360, 640, "clean"), (720, 1280, "iso3200")):
+        cases = [(180, 320, "iso3200"), (97, 132, "iso12800"), (360, 640, "clean"), (720, 1280, "iso3200")]
+        refs = []
+        for h, w, iso in cases:
             I0, I1 = synth.gray_pair(h, w, iso)
             ref, it_ref, _, _, _ = port.tvl1flow_traced(I0, I1, err_mode=0)
-            gray = torch.from_numpy(np.stack([I0, I1])).cuda()
-            flow, iters = b.tvl1_flow(gray, [1], [0], trace=True, check=True)
-            assert np.array_equal(iters[0, :it_ref.shape[0]].cpu().numpy(), it_ref), (h, w)
-            assert np.array_equal(flow[0].cpu().numpy(), ref), (h, w)
+            refs.append((torch.from_numpy(np.stack([I0, I1])).cuda(), ref, it_ref))
+        for mode, min_px in (("always", 0), ("always", 600000), ("never", -1), ("auto", -1), ("auto", -1)):
+            b.set_fuse(mode, min_px)
+            for (h, w, iso), (gray, ref, it_ref) in zip(cases, refs):
+                flow, iters = b.tvl1_flow(gray, [1], [0], trace=True, check=True)
+                assert np.array_equal(iters[0, :it_ref.shape[0]].cpu().numpy(), it_ref), (mode, min_px, h, w)
+                assert np.array_equal(flow[0].cpu().numpy(), ref), (mode, min_px, h, w)
     finally:
         b.close()
 

@@ -1,8 +1,11 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 20 --warmup 5 > gpurun_out/r2p_bench.json 2>/dev/null
-python bench.py --steps 8 --warmup 3 --no-cpu-baseline --noise clean > gpurun_out/r2p_clean.json 2>/dev/null
-python bench.py --steps 8 --warmup 3 --no-cpu-baseline --noise iso12800 > gpurun_out/r2p_iso12800.json 2>/dev/null
-python tools/time_single.py 2>&1 | tail -4 | cut -c1-220
-python tools/prof_solver.py 29 > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:solver_kernel -s 2 -c 1 -o gpurun_out/solver_r02c python tools/prof_solver.py 29 > gpurun_out/ncu.log 2>&1
-echo ncu_rc=$?
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+RVDD_FUSE=1 python -m pytest tests/test_gpu_parity.py tests/test_gpu_pipeline_configs.py -m gpu -x -q 2>&1 | tail -2
+for r in 1 2; do
+RVDD_FUSE=0 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/r2t_never_$r.json 2>/dev/null
+python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/r2t_auto_$r.json 2>/dev/null
+done
+for n in clean iso12800; do
+RVDD_FUSE=0 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --noise $n > gpurun_out/r2t_never_$n.json 2>/dev/null
+python bench.py --steps 8 --warmup 3 --no-cpu-baseline --noise $n > gpurun_out/r2t_auto_$n.json 2>/dev/null
+done

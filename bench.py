@@ -81,12 +81,16 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
+TRAFFIC_FILES = {False: "solver_kernel_r02c.txt", True: "solver_kernel_fused_r02d.txt"}
+
+
+def ncu_traffic(fused):
     """dram__bytes_read.sum + dram__bytes_write.sum of one solver launch of this very workload (29 pairs), from the
-    committed `ncu --set full` capture (profiles/solver_kernel_r02a.txt); None if the summary is missing."""
+    committed `ncu --set full` capture of the solver instantiation that ran (profiles/solver_kernel_*.txt); None if the
+    summary is missing."""
     try:
         tot = 0.0
-        for line in open(os.path.join(ROOT, "profiles", "solver_kernel_r02a.txt")):
+        for line in open(os.path.join(ROOT, "profiles", TRAFFIC_FILES[bool(fused)])):
             f = line.split()
             if f and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 tot += float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
@@ -241,6 +245,7 @@ def run_ours(args, rank, local_rank, world):
     clocks = sampler.finish()
     ms = e0.elapsed_time(e1)
     solver_ms = br.profile_read()
+    fused_kernel = br.last_solver_fused()
     scale_ms = br.profile_scales()
     phase_ms = br.profile_phases()
     br.profile(False)
@@ -377,9 +382,12 @@ def run_ours(args, rank, local_rank, world):
     sb = solver_bytes(sizes, iters)
     avg_solver_ms = sum(solver_ms) / max(1, len(solver_ms))
     achieved = sb / (avg_solver_ms * 1e-3) / 1e9 if avg_solver_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "rvdd::solver_kernel (persistent TV-L1 solver, 1 launch per step)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
-                "traffic_source": "profiles/solver_kernel_r02a.txt (ncu --set full of this workload, per launch)",
+    roofline = {"bound": "hbm",
+                "kernel": "rvdd::solver_kernel<%s> (persistent TV-L1 solver, 1 launch per step; %s)"
+                          % ("true" if fused_kernel else "false",
+                             "two iterations per pass on the finest level" if fused_kernel else "one iteration per pass"),
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(fused_kernel),
+                "traffic_source": "profiles/%s (ncu --set full of this workload, per launch)" % TRAFFIC_FILES[bool(fused_kernel)],
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": sb, "avg_launch_ms": avg_solver_ms,
                 "share_of_step": avg_solver_ms * args.steps / ms if ms > 0 else None,
                 "step_algorithmic_bytes": step_bytes(sizes, iters),

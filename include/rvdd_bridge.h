@@ -75,6 +75,8 @@ RVDD_API int rvdd_set_groups(rvdd_ctx *ctx, int n_groups);
  * iteration counts on this context; the default), 1 = never fuse, 2 = always.  min_px < 0 keeps the current threshold
  * (default 600000).  Environment RVDD_FUSE=auto|0|1 sets the initial mode. */
 RVDD_API int rvdd_set_fuse(rvdd_ctx *ctx, int mode, int min_px);
+/* 1 if the last rvdd_tvl1_flow_dev launch on this context used the two-iterations-per-pass instantiation, 0 if not. */
+RVDD_API int rvdd_last_solver_fused(rvdd_ctx *ctx);
 /* Watchdog of the persistent solver: a group barrier that waits longer than `ticks` SM clock cycles (default 4e9, about
  * 2 s; also settable with the environment variable RVDD_WATCHDOG_TICKS at context creation) makes the launch unwind.
  * Raise it under time-slicing / MPS / a debugger.  When it fires, every flow of that call is overwritten with NaN on

@@ -36,6 +36,7 @@ _SIGNATURES = {
     "rvdd_set_groups": (C.c_int, [C.c_void_p, C.c_int]),
     "rvdd_set_watchdog": (C.c_int, [C.c_void_p, C.c_longlong]),
     "rvdd_set_fuse": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "rvdd_last_solver_fused": (C.c_int, [C.c_void_p]),
     "rvdd_last_error": (C.c_char_p, []),
     "rvdd_abi_version": (C.c_int, []),
     "rvdd_gray_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -133,6 +134,10 @@ class Bridge:
         """Solver instantiation: 'auto' (default), 'never' or 'always' run two iterations per pass on levels of at least
         min_px pixels (rvdd_set_fuse).  Same bits either way."""
         self._ck(self.lib.rvdd_set_fuse(self.ctx, {"auto": 0, "never": 1, "always": 2}[mode], int(min_px)))
+
+    def last_solver_fused(self):
+        """True if the last tvl1_flow launch used the two-iterations-per-pass solver instantiation."""
+        return self.lib.rvdd_last_solver_fused(self.ctx) == 1
 
     def set_watchdog(self, ticks):
         """Solver watchdog in SM clock ticks (default 4e9); a launch whose watchdog fires returns NaN flows."""

@@ -193,6 +193,7 @@ struct rvdd_ctx {
     int fuse_mode = 0, fuse_min_px = 600000, fuse_first = 0;
     int *stat_host = nullptr;                   // pinned + mapped: 16 x (finest-level iterations per pair and warp) of the last launch
     int *stat_dev = nullptr;                    // its device alias
+    int last_fused = 0;                         // instantiation of the last launch (rvdd_last_solver_fused)
 };
 
 static int create_resources(rvdd_ctx *c)
@@ -293,6 +294,8 @@ extern "C" int rvdd_set_fuse(rvdd_ctx *c, int mode, int min_px)
     if (min_px >= 0) c->fuse_min_px = min_px;
     return 0;
 }
+
+extern "C" int rvdd_last_solver_fused(rvdd_ctx *c) { return c ? c->last_fused : -1; }
 
 extern "C" int rvdd_set_watchdog(rvdd_ctx *c, long long ticks)
 {
@@ -506,6 +509,7 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
     }
     const bool fused_kernel = c->fuse_mode == 2 || (c->fuse_mode == 0 && *(volatile int *)c->stat_host >= 4 * 16);
     CK(launch_solver(A, fused_kernel, st));
+    c->last_fused = fused_kernel ? 1 : 0;
     if (c->prof) {
         CK(cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st));
         c->prof_n++;

@@ -769,7 +769,9 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
                     // alone from the input buffers, which the fused pass leaves untouched.
                     int it = 0;
                     float err = INFINITY, err_before = INFINITY;
-                    const bool can_fuse = F2 && ((nx & 3) == 0) && n >= A.fuse_min_px;
+                    // the fused pass needs strips of some length to amortise its three halo rows: at least 16 rows per warp
+                    const bool can_fuse = F2 && ((nx & 3) == 0) && n >= A.fuse_min_px &&
+                                          ((nx + F2_OUT - 1) / F2_OUT) * ny >= 16 * gwarps;
                     while (err > A.eps2 && it < RVDD_MAX_ITERATIONS) {
                         IterPtrs P;
                         P.S = S; P.PL = PL; P.uc = uc; P.pc = pc;

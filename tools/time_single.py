@@ -1,10 +1,12 @@
-"""Where a single 1280x720 pair spends its time (whole GPU on one pair): python tools/time_single.py"""
+"""Where a single 1280x720 pair spends its time (whole GPU on one pair): python tools/time_single.py [never|always|auto]"""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from rvdd_release_b200 import bridge, synth
 br = bridge.default_bridge()
+if len(sys.argv) > 1:
+    br.set_fuse(sys.argv[1])
 for K in (1, 2, 4, 8):
     frames = synth.sequence(K + 1, 720, 1280, "iso3200", device="cuda")
     gray = br.gray(frames)

@@ -190,7 +190,7 @@ struct rvdd_ctx {
     // pass is launched when the previous launch on this context averaged at least 4 inner iterations per warp on the finest
     // level (noisy frames: ~19; clean frames: ~1.2, where the plain instantiation is faster) --, 1 = never, 2 = always.
     // Levels with fewer than fuse_min_px pixels always iterate one at a time.  Both kernels produce the same bits.
-    int fuse_mode = 0, fuse_min_px = 600000, fuse_first = 0;
+    int fuse_mode = 0, fuse_min_px = 600000, fuse_first = 0, fuse_min_rows = 64;
     int *stat_host = nullptr;                   // pinned + mapped: 16 x (finest-level iterations per pair and warp) of the last launch
     int *stat_dev = nullptr;                    // its device alias
     int last_fused = 0;                         // instantiation of the last launch (rvdd_last_solver_fused)
@@ -220,6 +220,7 @@ static int create_resources(rvdd_ctx *c)
     if (const char *env = getenv("RVDD_FUSE")) c->fuse_mode = (env[0] == 'a') ? 0 : (atoi(env) ? 2 : 1);   // auto | 0 | 1
     if (const char *env = getenv("RVDD_FUSE_MIN_PX")) c->fuse_min_px = atoi(env);     // tuning / A-B runs only
     if (const char *env = getenv("RVDD_FUSE_FIRST")) c->fuse_first = atoi(env);
+    if (const char *env = getenv("RVDD_FUSE_MIN_ROWS")) c->fuse_min_rows = atoi(env);
     CK(cudaHostAlloc((void **)&c->stat_host, sizeof(int), cudaHostAllocMapped));
     *c->stat_host = 0;
     CK(cudaHostGetDevicePointer((void **)&c->stat_dev, c->stat_host, 0));
@@ -496,6 +497,7 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
     A.spin_limit = c->spin_limit;
     A.fuse_min_px = c->fuse_min_px;
     A.fuse_first = c->fuse_first;
+    A.fuse_min_rows = c->fuse_min_rows;
     if (iters) CK(cudaMemsetAsync(iters, 0, sizeof(int) * (size_t)K * RVDD_TRACE_SCALES * p.nwarps, st));
     if (c->prof) {
         if ((int)c->prof_ev.size() < 2 * (c->prof_n + 1)) {
@@ -507,7 +509,11 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
         }
         CK(cudaEventRecord(c->prof_ev[2 * c->prof_n], st));
     }
-    const bool fused_kernel = c->fuse_mode == 2 || (c->fuse_mode == 0 && *(volatile int *)c->stat_host >= 4 * 16);
+    // auto: the fused instantiation only if the finest level can actually be fused with this group size (the kernel's own
+    // criterion), and the previous launch's inner loops were long
+    const bool fusable = (nx & 3) == 0 && (long long)nx * ny >= c->fuse_min_px &&
+                         (long long)((nx + 119) / 120) * ny >= (long long)c->fuse_min_rows * C * solver_threads() / 32;
+    const bool fused_kernel = c->fuse_mode == 2 || (c->fuse_mode == 0 && fusable && *(volatile int *)c->stat_host >= 4 * 16);
     CK(launch_solver(A, fused_kernel, st));
     c->last_fused = fused_kernel ? 1 : 0;
     if (c->prof) {

@@ -49,6 +49,7 @@ struct SolverArgs {
     long long spin_limit;               // watchdog, in clock64 ticks
     int fuse_min_px;                    // levels with at least this many pixels (and nx % 4 == 0) run two iterations per pass
     int fuse_first;                     // ... after this many single iterations of every inner loop
+    int fuse_min_rows;                  // ... and only if every warp of the group gets at least this many segment-rows
 };
 
 // bridge.cu: 2-D float32 TMA descriptor (dims d0 innermost / d1, row pitch in bytes, box b0 x b1, zero fill out of range)

@@ -769,9 +769,10 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
                     // alone from the input buffers, which the fused pass leaves untouched.
                     int it = 0;
                     float err = INFINITY, err_before = INFINITY;
-                    // the fused pass needs strips of some length to amortise its three halo rows: at least 16 rows per warp
+                    // the fused pass needs long strips to amortise its halo rows and its deeper pipeline: measured on 1280x720, it
+                    // wins with 132 rows per warp (29 pairs in flight) and loses with 35 (8 pairs)
                     const bool can_fuse = F2 && ((nx & 3) == 0) && n >= A.fuse_min_px &&
-                                          ((nx + F2_OUT - 1) / F2_OUT) * ny >= 16 * gwarps;
+                                          ((nx + F2_OUT - 1) / F2_OUT) * ny >= A.fuse_min_rows * gwarps;
                     while (err > A.eps2 && it < RVDD_MAX_ITERATIONS) {
                         IterPtrs P;
                         P.S = S; P.PL = PL; P.uc = uc; P.pc = pc;

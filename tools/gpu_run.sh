@@ -1,6 +1,7 @@
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_dropin.py -m gpu -x -q 2>&1 | tail -2
-for m in never auto always; do echo "== $m"; python tools/time_single.py $m 2>&1 | tail -4 | cut -c1-160; done
-python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/r2u_auto.json 2>/dev/null
-python tools/prof_solver.py 29 iso3200 always > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:solver_kernel -s 2 -c 1 -o gpurun_out/solver_r02d_fused python tools/prof_solver.py 29 iso3200 always > gpurun_out/ncu.log 2>&1
-echo ncu_rc=$?
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+echo "== auto"; python tools/time_single.py auto 2>&1 | tail -4 | cut -c1-100
+python bench.py --steps 20 --warmup 5 > gpurun_out/r2v_bench.json 2>/dev/null
+python bench.py --steps 8 --warmup 3 --no-cpu-baseline --noise clean > gpurun_out/r2v_clean.json 2>/dev/null
+python bench.py --steps 8 --warmup 3 --no-cpu-baseline --noise iso12800 > gpurun_out/r2v_iso12800.json 2>/dev/null
+python profiles/bench_precompute.py --seqs-per-gpu 12 > gpurun_out/r2v_c4_1gpu.json 2>/dev/null

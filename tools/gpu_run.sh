@@ -1,7 +1,11 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-echo "== auto"; python tools/time_single.py auto 2>&1 | tail -4 | cut -c1-100
-python bench.py --steps 20 --warmup 5 > gpurun_out/r2v_bench.json 2>/dev/null
-python bench.py --steps 8 --warmup 3 --no-cpu-baseline --noise clean > gpurun_out/r2v_clean.json 2>/dev/null
-python bench.py --steps 8 --warmup 3 --no-cpu-baseline --noise iso12800 > gpurun_out/r2v_iso12800.json 2>/dev/null
-python profiles/bench_precompute.py --seqs-per-gpu 12 > gpurun_out/r2v_c4_1gpu.json 2>/dev/null
+for r in 1 2; do
+for v in base f2call; do
+  if [ $v = base ]; then L=rvdd-release_b200/lib/libBridge.so; else L=rvdd-release_b200/lib/libBridge_$v.so; fi
+  RVDD_BRIDGE_LIB=$L python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/r2x_${v}_$r.json 2>/dev/null
+done; done
+for v in base f2call; do
+  if [ $v = base ]; then L=rvdd-release_b200/lib/libBridge.so; else L=rvdd-release_b200/lib/libBridge_$v.so; fi
+  RVDD_FUSE=1 RVDD_BRIDGE_LIB=$L python bench.py --steps 8 --warmup 3 --no-cpu-baseline --noise clean > gpurun_out/r2x_${v}_clean_forced.json 2>/dev/null
+done
+RVDD_BRIDGE_LIB=rvdd-release_b200/lib/libBridge_f2call.so python -m pytest tests/test_gpu_dropin.py -m gpu -x -q -k "instantiations" 2>&1 | tail -1

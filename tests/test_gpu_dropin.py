@@ -233,3 +233,32 @@ def test_flow_edge_cases_and_errors(bridge, port):
     ref = port.tvl1flow(c, c)
     flow = bridge.tvl1_flow(torch.from_numpy(np.stack([c, c])).cuda(), [1], [0], check=True)
     assert np.array_equal(flow[0].cpu().numpy(), ref) and np.count_nonzero(ref) == 0
+
+
+def test_auto_kernel_choice_follows_the_iteration_counts(libpath):
+    """'auto' launches the two-iterations-per-pass instantiation only when the previous launch's inner loops were long (noisy
+    frames) and the batch gives every warp long strips; clean frames and small batches stay on the plain kernel.  Either way
+    the result of a launch does not depend on which instantiation computed it."""
+    from rvdd_release_b200 import bridge as B
+    b = B.Bridge(libpath)
+    try:
+        noisy = b.gray(synth.sequence(17, 720, 1280, "iso3200", device="cuda"))
+        clean = b.gray(synth.sequence(17, 720, 1280, "clean", device="cuda"))
+        src, tgt = np.arange(16), np.arange(1, 17)
+        b.set_fuse("auto")
+        first = b.tvl1_flow(noisy, src, tgt)
+        assert not b.last_solver_fused()                       # nothing known yet: plain kernel
+        torch.cuda.synchronize()
+        second = b.tvl1_flow(noisy, src, tgt)
+        assert b.last_solver_fused()                           # ~19 inner iterations per warp on the finest level
+        assert torch.equal(first, second)
+        torch.cuda.synchronize()
+        b.tvl1_flow(noisy, src[:2], tgt[:2])
+        assert not b.last_solver_fused()                       # 2 pairs on the whole GPU: strips too short to fuse
+        torch.cuda.synchronize()
+        b.tvl1_flow(clean, src, tgt)                           # (still decided from the noisy launch before it)
+        torch.cuda.synchronize()
+        b.tvl1_flow(clean, src, tgt)
+        assert not b.last_solver_fused()                       # ~1 inner iteration per warp: plain kernel
+    finally:
+        b.close()

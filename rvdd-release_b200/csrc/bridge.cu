@@ -498,6 +498,7 @@ extern "C" int rvdd_tvl1_flow_dev(rvdd_ctx *c, const float *gray, int nframes, i
     A.fuse_min_px = c->fuse_min_px;
     A.fuse_first = c->fuse_first;
     A.fuse_min_rows = c->fuse_min_rows;
+    A.fuse_hint = *(volatile int *)c->stat_host / 16;
     if (iters) CK(cudaMemsetAsync(iters, 0, sizeof(int) * (size_t)K * RVDD_TRACE_SCALES * p.nwarps, st));
     if (c->prof) {
         if ((int)c->prof_ev.size() < 2 * (c->prof_n + 1)) {

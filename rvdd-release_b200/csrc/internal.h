@@ -50,6 +50,7 @@ struct SolverArgs {
     int fuse_min_px;                    // levels with at least this many pixels (and nx % 4 == 0) run two iterations per pass
     int fuse_first;                     // ... after this many single iterations of every inner loop
     int fuse_min_rows;                  // ... and only if every warp of the group gets at least this many segment-rows
+    int fuse_hint;                      // inner iterations per warp on the finest level in the previous launch (0 = unknown)
 };
 
 // bridge.cu: 2-D float32 TMA descriptor (dims d0 innermost / d1, row pitch in bytes, box b0 x b1, zero fill out of range)

@@ -754,7 +754,8 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) solver_kernel
                 if (!group_sync(g, &s_flag)) return;
 
                 unsigned long long ns_consts = 0ULL, ns_iter = 0ULL;
-                int prev_iters = 0;                      // iterations of this level's previous warp (fused-pass policy)
+                int prev_iters = A.fuse_hint;            // iterations of this level's previous warp (fused-pass policy); for the
+                                                         // first warp: the finest-level average of the previous launch
                 for (int w = 0; w < A.nwarps; w++) {
                     const unsigned long long tp0 = stamping ? now_ns() : 0ULL;
                     // ---- warp constants (:143-159): bicubic samples of I1, I1x, I1y at x + u

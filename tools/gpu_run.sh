@@ -1,7 +1,5 @@
 mkdir -p gpurun_out
-for r in 1 2 3; do
-for v in prev base; do
-  if [ $v = base ]; then L=rvdd-release_b200/lib/libBridge.so; else L=rvdd-release_b200/lib/libBridge_$v.so; fi
-  RVDD_BRIDGE_LIB=$L python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/r2y_${v}_$r.json 2>/dev/null
-done; done
-python -m pytest tests/test_gpu_dropin.py tests/test_gpu_parity.py -m gpu -x -q -k "flow or instantiations or auto" 2>&1 | tail -1
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:solver_kernel|warp_|gauss_|resample_|gray_|minmax_|setup_|interleave_|poison_|demosaic_|upsample2_|remosaick" -c 300 --csv --log-file gpurun_out/launches_r02.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu.log 2>&1
+echo ncu_rc=$?
+python bench.py --steps 20 --warmup 5 > gpurun_out/r2z_bench.json 2>/dev/null

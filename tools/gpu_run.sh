@@ -1,5 +1,3 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:solver_kernel|warp_|gauss_|resample_|gray_|minmax_|setup_|interleave_|poison_|demosaic_|upsample2_|remosaick" -c 300 --csv --log-file gpurun_out/launches_r02.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu.log 2>&1
-echo ncu_rc=$?
-python bench.py --steps 20 --warmup 5 > gpurun_out/r2z_bench.json 2>/dev/null
+RVDD_FUSE_MIN_ROWS=1 python tools/memcheck_case.py > gpurun_out/plain.log 2>&1 && RVDD_FUSE_MIN_ROWS=1 timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python tools/memcheck_case.py > gpurun_out/memcheck_r02.log 2>&1
+echo rc=$?; tail -8 gpurun_out/memcheck_r02.log

@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-RVDD_FUSE_MIN_ROWS=1 python tools/memcheck_case.py > gpurun_out/plain.log 2>&1 && RVDD_FUSE_MIN_ROWS=1 timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python tools/memcheck_case.py > gpurun_out/memcheck_r02.log 2>&1
-echo rc=$?; tail -8 gpurun_out/memcheck_r02.log
+for v in base t256c1 t320c1; do
+  if [ $v = base ]; then L=rvdd-release_b200/lib/libBridge.so; else L=rvdd-release_b200/lib/libBridge_$v.so; fi
+  RVDD_BRIDGE_LIB=$L python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/r3a_${v}.json 2>/dev/null
+done

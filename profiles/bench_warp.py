@@ -40,7 +40,8 @@ def torch_warp(x, flow):
 
 
 rows = []
-for (B, C, H, W) in [(1, 3, 1440, 2560), (1, 48, 1440, 2560), (4, 48, 720, 1280), (29, 4, 720, 1280)]:
+ONLY_HWC = "--hwc-only" in sys.argv                       # python profiles/bench_warp.py --hwc-only: the HWC section alone
+for (B, C, H, W) in ([] if ONLY_HWC else [(1, 3, 1440, 2560), (1, 48, 1440, 2560), (4, 48, 720, 1280), (29, 4, 720, 1280)]):
     x = torch.randn(B, C, H, W, device="cuda")
     yy, xx = torch.meshgrid(torch.arange(H, device="cuda", dtype=torch.float32), torch.arange(W, device="cuda", dtype=torch.float32), indexing="ij")
     flow = torch.stack((5.0 + 3.0 * torch.sin(yy / 97.0), -3.0 + 2.0 * torch.cos(xx / 131.0)), 0)[None].repeat(B, 1, 1, 1).contiguous()
@@ -69,12 +70,15 @@ for (B, C, H, W) in [(29, 4, 720, 1280), (8, 4, 1080, 1920)]:
     t_full = timeit(lambda: br.warp(x, flow, "bicubic", want_mask=False, out=out))
     t_rough = timeit(lambda: br.warp(x, rough, "bicubic", want_mask=False, out=out))
     t_bil = timeit(lambda: br.warp(x, flow, "bilinear", want_mask=False, out=out))
+    smooth = torch.stack((5.0 + 3.0 * torch.sin(yy / 97.0), -3.0 + 2.0 * torch.cos(xx / 131.0)), 0)[None].repeat(B, 1, 1, 1).contiguous()
+    t_smooth = timeit(lambda: br.warp(x, smooth, "bicubic", want_mask=False, out=out))
     rows.append(dict(layout="HWC", shape=[B, C, H, W], ms=t_full, gbs=by / t_full / 1e6, frac=by / t_full / 1e6 / peak,
-                     ms_white_noise_flow=t_rough, ms_bilinear=t_bil, tma=bool(os.environ.get("RVDD_WARP_TMA"))))
+                     ms_white_noise_flow=t_rough, ms_noise_free_flow=t_smooth, ms_bilinear=t_bil, tma=bool(os.environ.get("RVDD_WARP_TMA")),
+                     one_px_per_thread=bool(os.environ.get("RVDD_WARP_HWC_1PX"))))
     print(json.dumps(rows[-1]))
 
 # Hamilton-Adams demosaic (csrc/demosaic.cu): 4 B read + 12 B written per full-resolution pixel
-for (B, H, W) in [(1, 720, 1280), (8, 720, 1280), (1, 1080, 1920)]:
+for (B, H, W) in ([] if ONLY_HWC else [(1, 720, 1280), (8, 720, 1280), (1, 1080, 1920)]):
     x = torch.rand(B, 4, H, W, device="cuda") * 2 - 1
     by = 16.0 * B * 4 * H * W
     t = timeit(lambda: br.demosaic(x, "gbrg"))

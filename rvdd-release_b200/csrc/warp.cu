@@ -380,6 +380,93 @@ __global__ void __launch_bounds__(256) warp_hwc4_kernel(const WarpArgs a)
     }
 }
 
+// Bicubic, TWO vertically adjacent pixels per thread: the arithmetic of warp_hwc4_kernel unchanged, both sample positions
+// (flow loads) first, then one pixel after the other.  Measured on 29 x (720, 1280, 4), B200 (profiles/warp_hwc_variants_r02.txt):
+// 0.431 -> 0.403 ms (white-noise flow 0.816 -> 0.688 ms).  The kernel is latency-bound and sensitive to the schedule, not
+// to the number of L1 look-ups -- every "smarter" variant lost:
+//   * SHARING taps between the two pixels (their windows overlap in 3 of 4 rows when the flow is smooth: 20 loads for 32):
+//     paired along x the lanes stride 32 bytes, 0.591 ms; paired along y, 0.394 ms on a noise-free flow but 0.493 ms as soon
+//     as a few per cent of the lanes leave the shared path (0.430 ms when whole warps must agree);
+//   * 3 or 4 pixels per thread: 0.441 / 0.500 ms;  taller tiles (512 or 1024 threads, 16 .. 64 rows): 0.46 .. 0.65 ms;
+//   * TMA-staged tiles (below): 0.55 ms.
+__device__ __forceinline__ void hwc4_sample_pos(const WarpArgs &a, int b, int x, int y, float &ix, float &iy)
+{
+    float fu, fv;
+    const float *fl = a.flow + (long long)b * 2 * a.fh * a.fw;
+    if (a.fh == a.H && a.fw == a.W) {
+        fu = fl[(long long)y * a.W + x];
+        fv = fl[(long long)a.H * a.W + (long long)y * a.W + x];
+    } else {
+        const float sy = a.H > 1 ? (float)(a.fh - 1) / (float)(a.H - 1) : 0.f;
+        const float sx = a.W > 1 ? (float)(a.fw - 1) / (float)(a.W - 1) : 0.f;
+        fu = up2_sample(fl, a.fh, a.fw, y, x, sy, sx);
+        fv = up2_sample(fl + (long long)a.fh * a.fw, a.fh, a.fw, y, x, sy, sx);
+    }
+    fu *= a.flow_mul;
+    fv *= a.flow_mul;
+    const float gxn = 2.0f * ((float)x + fu) / (float)(a.W - 1) - 1.0f;
+    const float gyn = 2.0f * ((float)y + fv) / (float)(a.H - 1) - 1.0f;
+    if (a.mask)
+        a.mask[((long long)b * a.H + y) * a.W + x] = (gxn >= -1.f && gxn <= 1.f && gyn >= -1.f && gyn <= 1.f) ? 1.f : 0.f;
+    ix = ((gxn + 1.f) / 2.f) * (float)(a.W - 1);
+    iy = ((gyn + 1.f) / 2.f) * (float)(a.H - 1);
+}
+
+__device__ __forceinline__ void hwc4_store(const WarpArgs &a, int b, int x, int y, const float4 &acc)
+{
+    float *ob = a.out + (long long)b * a.os_b + (long long)y * a.os_h + (long long)x * a.os_w;
+    if (a.os_c == 1 && ((reinterpret_cast<uintptr_t>(ob) & 15) == 0)) {
+        *reinterpret_cast<float4 *>(ob) = acc;
+    } else {
+        ob[0] = acc.x; ob[a.os_c] = acc.y; ob[2 * a.os_c] = acc.z; ob[3 * a.os_c] = acc.w;
+    }
+}
+
+#define HWC4_ROW(ACC, V0, V1, V2, V3, CX, CYR)                                                                  \
+    ACC.x += (V0.x * CX[0] + V1.x * CX[1] + V2.x * CX[2] + V3.x * CX[3]) * (CYR);                               \
+    ACC.y += (V0.y * CX[0] + V1.y * CX[1] + V2.y * CX[2] + V3.y * CX[3]) * (CYR);                               \
+    ACC.z += (V0.z * CX[0] + V1.z * CX[1] + V2.z * CX[2] + V3.z * CX[3]) * (CYR);                               \
+    ACC.w += (V0.w * CX[0] + V1.w * CX[1] + V2.w * CX[2] + V3.w * CX[3]) * (CYR);
+
+__device__ __forceinline__ float4 hwc4_bicubic_px(const WarpArgs &a, const float4 *xb, long long rowq, float ix, float iy)
+{
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    float cx[4], cy[4];
+    cubic_coeffs(ix - fx0, cx);
+    cubic_coeffs(iy - fy0, cy);
+    int ox[4];
+    long long oy[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        ox[k] = (int)fminf((float)(a.W - 1), fmaxf(fx0 - 1.f + (float)k, 0.f));
+        oy[k] = (long long)(int)fminf((float)(a.H - 1), fmaxf(fy0 - 1.f + (float)k, 0.f)) * rowq;
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const float4 *q = xb + oy[r];
+        const float4 v0 = __ldg(q + ox[0]), v1 = __ldg(q + ox[1]), v2 = __ldg(q + ox[2]), v3 = __ldg(q + ox[3]);
+        HWC4_ROW(acc, v0, v1, v2, v3, cx, cy[r])
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(256) warp_hwc4_2rows_kernel(const WarpArgs a)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = 2 * (blockIdx.y * 8 + (threadIdx.x >> 5));
+    const int b = blockIdx.z;
+    if (x >= a.W || y >= a.H) return;
+    const bool two = y + 1 < a.H;
+    float ix0, iy0, ix1 = 0.f, iy1 = 0.f;
+    hwc4_sample_pos(a, b, x, y, ix0, iy0);
+    if (two) hwc4_sample_pos(a, b, x, y + 1, ix1, iy1);
+    const float4 *xb = reinterpret_cast<const float4 *>(a.x + (long long)b * a.xs_b);
+    const long long rowq = a.xs_h >> 2;                 // row pitch in float4 units
+    hwc4_store(a, b, x, y, hwc4_bicubic_px(a, xb, rowq, ix0, iy0));
+    if (two) hwc4_store(a, b, x, y + 1, hwc4_bicubic_px(a, xb, rowq, ix1, iy1));
+}
+
 // ------------------------------------------------------------------------------------------------ HWC, 4 channels, TMA-staged
 //
 // OPT-IN (environment RVDD_WARP_TMA=1): measured SLOWER than the L1 gathers of warp_hwc4_kernel on B200 -- 29 x (720, 1280, 4):
@@ -552,10 +639,16 @@ cudaError_t launch_warp(const WarpArgs &a, cudaStream_t st)
                 return cudaGetLastError();
             }
         }
-        if (a.interp == 1)
-            warp_hwc4_kernel<1><<<grid, 256, 0, st>>>(a);
-        else
+        if (a.interp == 1) {
+            static const bool one_px = getenv("RVDD_WARP_HWC_1PX") != nullptr;      // A/B switch: one pixel per thread
+            if (one_px) {
+                warp_hwc4_kernel<1><<<grid, 256, 0, st>>>(a);
+            } else {
+                warp_hwc4_2rows_kernel<<<dim3(grid.x, (a.H + 15) / 16, grid.z), 256, 0, st>>>(a);
+            }
+        } else {
             warp_hwc4_kernel<0><<<grid, 256, 0, st>>>(a);
+        }
         return cudaGetLastError();
     }
     if (a.xs_w == 1 && a.C >= 3) {                      // plane-contiguous input: staged gathers

@@ -1,6 +1,5 @@
 mkdir -p gpurun_out
-python profiles/bench_warp.py --hwc-only > gpurun_out/w5_2rows.jsonl 2>gpurun_out/w5.err
-RVDD_WARP_HWC_1PX=1 python profiles/bench_warp.py --hwc-only > gpurun_out/w5_1px.jsonl 2>>gpurun_out/w5.err
-cat gpurun_out/w5_2rows.jsonl gpurun_out/w5_1px.jsonl
-python -m pytest tests -m gpu -x -q > gpurun_out/w5_pytest.log 2>&1; echo "pytest rc $?"; tail -1 gpurun_out/w5_pytest.log
-python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/w5_bench.json 2>gpurun_out/w5_bench.err; cat gpurun_out/w5_bench.json
+for v in "" _f2dhw; do
+  RVDD_BRIDGE_LIB=rvdd-release_b200/lib/libBridge$v.so python tools/time_wc.py 2>&1 | tail -1 | tee -a gpurun_out/f2d_wc.txt
+done
+python -m pytest tests/test_gpu_dropin.py tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3

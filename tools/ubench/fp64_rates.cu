@@ -21,7 +21,6 @@ __global__ void rate_kernel(int iters, double seed, float fseed, double *sink, l
             if (OP == 1) x[k] = __dmul_rn(x[k], seed);
             if (OP == 2) x[k] = __fma_rn(x[k], seed, seed);
             if (OP == 3) { x[k] = (double)f[k]; f[k] = __int_as_float(__float_as_int(f[k]) + (int)__double2hiint(x[k])); }   // F2F.F64.F32 + 1 IADD
-            if (OP == 4) { f[k] = __int_as_float(__float_as_int(f[k]) + (int)__double2hiint(x[k])); }                         // the IADD alone
             if (OP == 5) { f[k] = __double2float_rn(x[k]); x[k] = __hiloint2double(__float_as_int(f[k]), __double2loint(x[k])); }   // F2F.F32.F64
             if (OP == 6) { x[k] = __dadd_rn(x[k], seed); f[k] = __fadd_rn(f[k], fseed); }                                      // DADD + FADD
         }
@@ -62,7 +61,6 @@ int main()
         run<1>("DMUL", w, p.multiProcessorCount);
         run<2>("DFMA", w, p.multiProcessorCount);
         run<3>("F2F.F64.F32 (+IADD)", w, p.multiProcessorCount);
-        run<4>("IADD alone", w, p.multiProcessorCount);
         run<5>("F2F.F32.F64 (+mov)", w, p.multiProcessorCount);
         run<6>("DADD + FADD pairs (DADD count)", w, p.multiProcessorCount);
     }

@@ -40,8 +40,9 @@ def torch_warp(x, flow):
 
 
 rows = []
+ONLY_DM = "--demosaic-only" in sys.argv
 ONLY_HWC = "--hwc-only" in sys.argv                       # python profiles/bench_warp.py --hwc-only: the HWC section alone
-for (B, C, H, W) in ([] if ONLY_HWC else [(1, 3, 1440, 2560), (1, 48, 1440, 2560), (4, 48, 720, 1280), (29, 4, 720, 1280)]):
+for (B, C, H, W) in ([] if ONLY_HWC or ONLY_DM else [(1, 3, 1440, 2560), (1, 48, 1440, 2560), (4, 48, 720, 1280), (29, 4, 720, 1280)]):
     x = torch.randn(B, C, H, W, device="cuda")
     yy, xx = torch.meshgrid(torch.arange(H, device="cuda", dtype=torch.float32), torch.arange(W, device="cuda", dtype=torch.float32), indexing="ij")
     flow = torch.stack((5.0 + 3.0 * torch.sin(yy / 97.0), -3.0 + 2.0 * torch.cos(xx / 131.0)), 0)[None].repeat(B, 1, 1, 1).contiguous()
@@ -59,7 +60,7 @@ for (B, C, H, W) in ([] if ONLY_HWC else [(1, 3, 1440, 2560), (1, 48, 1440, 2560
     print(json.dumps(rows[-1]))
 
 # (H, W, 4) frames in their on-disk layout (channel innermost): the warp of the headline step (compute_flow_and_warp)
-for (B, C, H, W) in [(29, 4, 720, 1280), (8, 4, 1080, 1920)]:
+for (B, C, H, W) in ([] if ONLY_DM else [(29, 4, 720, 1280), (8, 4, 1080, 1920)]):
     x = torch.randn(B, H, W, C, device="cuda").permute(0, 3, 1, 2)
     yy, xx = torch.meshgrid(torch.arange(H, device="cuda", dtype=torch.float32), torch.arange(W, device="cuda", dtype=torch.float32), indexing="ij")
     flow = torch.stack((5.0 + 3.0 * torch.sin(yy / 97.0), -3.0 + 2.0 * torch.cos(xx / 131.0)), 0)[None].repeat(B, 1, 1, 1).contiguous()
@@ -85,5 +86,5 @@ for (B, H, W) in ([] if ONLY_HWC else [(1, 720, 1280), (8, 720, 1280), (1, 1080,
     rgb = br.demosaic(x, "gbrg")
     t2 = timeit(lambda: br.remosaick_gray(rgb, "gbrg"))
     rows.append(dict(kernel="demosaic_ha", packed_shape=[B, 4, H, W], ms=t, gbs=by / t / 1e6, frac=by / t / 1e6 / peak,
-                     remosaick_gray_ms=t2, remosaick_gray_gbs=(4.0 * B * H * W * 5) / t2 / 1e6))
+                     general_path_only=bool(os.environ.get("RVDD_DEMOSAIC_GENERAL")), remosaick_gray_ms=t2, remosaick_gray_gbs=(4.0 * B * H * W * 5) / t2 / 1e6))
     print(json.dumps(rows[-1]))

@@ -213,8 +213,7 @@ cudaError_t launch_demosaic_ha(const float *x, float *y, int B, int H, int W, in
 {
     DemosaicArgs a;
     a.x = x; a.y = y; a.B = B; a.H = H; a.W = W;
-    static const int general = getenv("RVDD_DEMOSAIC_GENERAL") != nullptr;
-    a.force_general = general;
+    a.force_general = getenv("RVDD_DEMOSAIC_GENERAL") != nullptr;       // read per call: tests flip it
     if (by != 1 - ry || bx != 1 - rx) return cudaErrorInvalidValue;        // red and blue sit on a diagonal of the cell
     const dim3 grid((2 * W + DM_TW - 1) / DM_TW, (2 * H + DM_TH - 1) / DM_TH, B);
     switch (ry * 2 + rx) {

@@ -640,7 +640,7 @@ cudaError_t launch_warp(const WarpArgs &a, cudaStream_t st)
             }
         }
         if (a.interp == 1) {
-            static const bool one_px = getenv("RVDD_WARP_HWC_1PX") != nullptr;      // A/B switch: one pixel per thread
+            const bool one_px = getenv("RVDD_WARP_HWC_1PX") != nullptr;             // A/B switch (read per call): one pixel per thread
             if (one_px) {
                 warp_hwc4_kernel<1><<<grid, 256, 0, st>>>(a);
             } else {

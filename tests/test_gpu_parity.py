@@ -443,3 +443,29 @@ def test_warp_hwc4_tma_staged_variant(bridge, monkeypatch, interp):
     monkeypatch.delenv("RVDD_WARP_TMA")
     y2, _ = bridge.warp(xc.cuda(), flow.cuda(), interp)
     assert rel_err(y2.cpu().numpy(), ref.numpy()) <= WARP_RTOL
+
+
+def test_kernel_variants_are_bit_equal(bridge, monkeypatch):
+    """The shipped fast paths against the plain ones they replaced, bit for bit: demosaic interior tiles vs the general
+    border path (RVDD_DEMOSAIC_GENERAL=1), (H, W, 4) bicubic warp two rows per thread vs one pixel per thread
+    (RVDD_WARP_HWC_1PX=1).  Sizes with interior tiles, ragged edges, odd widths and a misaligned view."""
+    g = torch.Generator().manual_seed(11)
+    for (B, H, W) in [(2, 100, 136), (1, 37, 65), (1, 64, 70)]:
+        x = (torch.rand(B, 4, H, W, generator=g) * 2 - 1).cuda()
+        flat = torch.zeros(B * 4 * H * W + 1, device="cuda")
+        flat[1:] = x.reshape(-1)
+        views = [x, flat[1:].view(B, 4, H, W)]                 # the second: rows not 8-byte aligned -> scalar staging
+        for pat in ("gbrg", "rggb"):
+            fast = [bridge.demosaic(v, pat).cpu() for v in views]
+            monkeypatch.setenv("RVDD_DEMOSAIC_GENERAL", "1")
+            general = bridge.demosaic(x, pat).cpu()
+            monkeypatch.delenv("RVDD_DEMOSAIC_GENERAL")
+            assert torch.equal(fast[0], general) and torch.equal(fast[1], general)
+    for (B, H, W) in [(2, 75, 150), (1, 33, 31), (1, 2, 40)]:
+        x = torch.randn(B, H, W, 4, generator=g).cuda().permute(0, 3, 1, 2)
+        for flow in (2.5 + 0.05 * torch.randn(B, 2, H, W, generator=g), 5.0 * torch.randn(B, 2, H, W, generator=g)):
+            two, m2 = bridge.warp(x, flow.cuda(), "bicubic")
+            monkeypatch.setenv("RVDD_WARP_HWC_1PX", "1")
+            one, m1 = bridge.warp(x, flow.cuda(), "bicubic")
+            monkeypatch.delenv("RVDD_WARP_HWC_1PX")
+            assert torch.equal(two, one) and torch.equal(m2, m1)

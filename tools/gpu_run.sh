@@ -1,2 +1,2 @@
-python profiles/bench_warp.py --demosaic-only | cut -c1-140
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_pipeline.py tests/test_gpu_pipeline_configs.py -m gpu -x -q 2>&1 | tail -2
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2

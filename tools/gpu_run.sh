@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
-python tools/prof_stage.py hwc4 && \
-ncu --set full --clock-control none --import-source on -k regex:warp_hwc4 -s 2 -c 1 -f -o gpurun_out/warp_hwc4_r02 python tools/prof_stage.py hwc4 > gpurun_out/ncu_warp4.log 2>&1
-echo "rc $?"; tail -3 gpurun_out/ncu_warp4.log
+for v in _wcp_b4 _wcp_b1 _wcp_nod; do
+  RVDD_BRIDGE_LIB=rvdd-release_b200/lib/libBridge$v.so python tools/time_wc.py 2>&1 | tail -1 | tee -a gpurun_out/wcp2.txt
+done
+RVDD_WC_PLANES=0 RVDD_BRIDGE_LIB=rvdd-release_b200/lib/libBridge_wcp_b4.so python tools/time_wc.py 2>&1 | tail -1 | tee -a gpurun_out/wcp2.txt

@@ -1,5 +1,4 @@
 mkdir -p gpurun_out
-for v in _wcp_b4 _wcp_b1 _wcp_nod; do
-  RVDD_BRIDGE_LIB=rvdd-release_b200/lib/libBridge$v.so python tools/time_wc.py 2>&1 | tail -1 | tee -a gpurun_out/wcp2.txt
-done
-RVDD_WC_PLANES=0 RVDD_BRIDGE_LIB=rvdd-release_b200/lib/libBridge_wcp_b4.so python tools/time_wc.py 2>&1 | tail -1 | tee -a gpurun_out/wcp2.txt
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ll_plain.json 2>gpurun_out/ll_plain.err && \
+ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:solver_kernel|warp_|gauss_|resample_|gray_|minmax_|setup_|interleave_|poison_|demosaic_|upsample2_|remosaick" -c 300 --csv --log-file gpurun_out/launches_r02e.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ll_ncu.log 2>&1
+echo "rc $?"; wc -l gpurun_out/launches_r02e.csv

@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-python bench.py --noise clean --no-cpu-baseline > gpurun_out/fin_clean.json 2>gpurun_out/fin_clean.err; echo "rc $?"
-python bench.py --noise iso12800 --no-cpu-baseline > gpurun_out/fin_12800.json 2>gpurun_out/fin_12800.err; echo "rc $?"
-python tools/show.py gpurun_out/fin_clean.json | head -2; python tools/show.py gpurun_out/fin_12800.json | head -2
+python tools/time_sizes.py | tee gpurun_out/sizes_default.jsonl
+RVDD_FUSE_MIN_PX=200000 python tools/time_sizes.py | tee gpurun_out/sizes_fuse200k.jsonl
+RVDD_FUSE_MIN_PX=200000 RVDD_FUSE_MIN_ROWS=32 python tools/time_sizes.py | tee gpurun_out/sizes_fuse200k_r32.jsonl

@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from rvdd_release_b200 import bridge, synth
 br = bridge.default_bridge()
-for (h, w, npairs) in [(360, 640, 116), (1080, 1920, 14), (2160, 3840, 8)]:
+for (h, w, npairs) in [(360, 640, 148), (360, 640, 116), (1080, 1920, 14), (2160, 3840, 8)]:
     frames = synth.sequence(npairs + 1, h, w, "iso3200", device="cuda")
     src, tgt = np.arange(npairs, dtype=np.int32), np.arange(1, npairs + 1, dtype=np.int32)
     def step():
@@ -21,5 +21,5 @@ for (h, w, npairs) in [(360, 640, 116), (1080, 1920, 14), (2160, 3840, 8)]:
     b.record(); torch.cuda.synchronize()
     ms = a.elapsed_time(b) / 3
     br.check()
-    print(json.dumps({"size": [w, h], "pairs_per_batch": npairs, "ms_per_batch": ms, "pairs_per_s": npairs / ms * 1e3,
+    print(json.dumps({"fused_kernel": br.last_solver_fused(), "fuse_min_px": os.environ.get("RVDD_FUSE_MIN_PX", "default"), "size": [w, h], "pairs_per_batch": npairs, "ms_per_batch": ms, "pairs_per_s": npairs / ms * 1e3,
                       "mpix_per_s": npairs * h * w / ms / 1e3}))

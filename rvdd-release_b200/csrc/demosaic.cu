@@ -23,6 +23,7 @@ namespace rvdd {
 #define DM_GW (DM_TW + 4)             // green tile: 2 columns of halo on each side (1 used), 1 row
 #define DM_GH (DM_TH + 2)
 #define DM_GX 2
+#define DM_GC (DM_TW / 2 + 1)           // compact green tile (red / blue positions only): columns per row
 
 struct DemosaicArgs {
     const float *x;                   // [B][4][H][W] packed raw
@@ -51,21 +52,29 @@ template <int PW> __device__ __forceinline__ float green_at(const float *p)
 // neighbour contributes its CFA value if it lies inside the image and zero if the padding replicated a pixel of another
 // colour -- at a pixel whose neighbours in that direction carry the colour, "outside the image" is exactly that case.
 // EDGE = false: the tile lies inside the image with its halo, every neighbour exists and the selects disappear.
-template <int RY, int RX, bool EDGE>
+// COMPACT: the green tile holds only the red / blue positions (the only ones ever read), DM_GC per row, column
+// (c + 1) >> 1 for tile column c: the lanes of a warp then read consecutive words instead of every other one (2-way bank
+// conflicts); g0 points at row 0 / compact column `lane` of the cell.  Otherwise g0 points at the cell's pixel (0, 0) in
+// the full-resolution green tile.
+template <int RY, int RX, bool EDGE, bool COMPACT>
 __device__ __forceinline__ void dm_cell(const float *p0, const float *g0, bool up, bool left, bool down, bool right,
                                         float (&red)[2][2], float (&grn)[2][2], float (&blu)[2][2])
 {
     constexpr int BY = 1 - RY, BX = 1 - RX;
+    // green at cell-relative (row, col): col in -1 .. 2
+    auto G_ = [&](int row, int col) -> float {
+        return COMPACT ? g0[row * DM_GC + ((col + 1) >> 1)] : g0[row * DM_GW + col];
+    };
     // the pixel that carries colour A sees colour B on its four diagonals: B there from the diagonal colour differences
     auto diag = [&](int py, int px, float &outB) {
         const float *p = p0 + py * DM_PW + px;
-        const float *g = g0 + py * DM_GW + px;
         const bool t = (!EDGE || py) ? true : up, bm = (EDGE && py) ? down : true;
         const bool l = (!EDGE || px) ? true : left, r = (EDGE && px) ? right : true;
         const float a00 = (t && l) ? p[-DM_PW - 1] : 0.f, a22 = (bm && r) ? p[DM_PW + 1] : 0.f;
         const float a02 = (t && r) ? p[-DM_PW + 1] : 0.f, a20 = (bm && l) ? p[DM_PW - 1] : 0.f;
-        const float gc = g[0];
-        const float gdp = (g[-DM_GW - 1] + -2.f * gc) + g[DM_GW + 1], gdn = (g[-DM_GW + 1] + -2.f * gc) + g[DM_GW - 1];
+        const float gc = G_(py, px);
+        const float gdp = (G_(py - 1, px - 1) + -2.f * gc) + G_(py + 1, px + 1);
+        const float gdn = (G_(py - 1, px + 1) + -2.f * gc) + G_(py + 1, px - 1);
         const float cp = (0.5f * a00 + 0.5f * a22) - gdp / 4.f, cn = (0.5f * a02 + 0.5f * a20) - gdn / 4.f;
         const float clp = fabsf(-a00 + a22) + fabsf(gdp), cln = fabsf(-a02 + a20) + fabsf(gdn);
         const float s = sgn(clp - cln);
@@ -75,12 +84,12 @@ __device__ __forceinline__ void dm_cell(const float *p0, const float *g0, bool u
     // a green pixel: the colour of its row from the horizontal neighbours, the colour of its column from the vertical ones
     auto cross = [&](int py, int px, float &outRow, float &outCol) {
         const float *p = p0 + py * DM_PW + px;
-        const float *g = g0 + py * DM_GW + px;
         const bool t = (!EDGE || py) ? true : up, bm = (EDGE && py) ? down : true;
         const bool l = (!EDGE || px) ? true : left, r = (EDGE && px) ? right : true;
         const float gc = p[0];                                   // green sample of the CFA
         // at the image border the replicated neighbour is this very pixel: its green is the sample itself
-        const float gl = l ? g[-1] : gc, grr = r ? g[1] : gc, gu = t ? g[-DM_GW] : gc, gd = bm ? g[DM_GW] : gc;
+        const float gl = l ? G_(py, px - 1) : gc, grr = r ? G_(py, px + 1) : gc;
+        const float gu = t ? G_(py - 1, px) : gc, gd = bm ? G_(py + 1, px) : gc;
         const float gdh = (0.25f * gl + -0.5f * gc) + 0.25f * grr;
         const float gdv = (0.25f * gu + -0.5f * gc) + 0.25f * gd;
         outRow = (0.5f * (l ? p[-1] : 0.f) + 0.5f * (r ? p[1] : 0.f)) - gdh;
@@ -147,9 +156,10 @@ __global__ void __launch_bounds__(256, 8) demosaic_ha_kernel(const DemosaicArgs 
             }
         }
         __syncthreads();
-        // ---- phase 2: the two red / blue pixels of the own cell, then the ring around the tile
-        g0[RY * DM_GW + RX] = green_at<DM_PW>(p0 + RY * DM_PW + RX);
-        g0[BY * DM_GW + BX] = green_at<DM_PW>(p0 + BY * DM_PW + BX);
+        // ---- phase 2: the two red / blue pixels of the own cell, then the ring around the tile; compact green tile
+        float *gc0 = &G[0][0] + (2 * wrp + 1) * DM_GC + lane;     // tile row 0 of the cell, compact column of tile column 2 * lane - 1
+        gc0[RY * DM_GC + ((RX + 1) >> 1)] = green_at<DM_PW>(p0 + RY * DM_PW + RX);
+        gc0[BY * DM_GC + ((BX + 1) >> 1)] = green_at<DM_PW>(p0 + BY * DM_PW + BX);
         if (threadIdx.x < 2 * (DM_TW + 2) + 2 * DM_TH) {
             int ry, rx;                                          // tile-relative position on the ring
             const int t = threadIdx.x;
@@ -158,10 +168,10 @@ __global__ void __launch_bounds__(256, 8) demosaic_ha_kernel(const DemosaicArgs 
             else if (t < 2 * (DM_TW + 2) + DM_TH) { ry = t - 2 * (DM_TW + 2); rx = -1; }
             else { ry = t - 2 * (DM_TW + 2) - DM_TH; rx = DM_TW; }
             if (((ry ^ rx) & 1) == rb)                           // X0, Y0 even: the parity inside the tile is the parity in the image
-                G[ry + 1][rx + DM_GX] = green_at<DM_PW>(&P[ry + 3][rx + DM_PX]);
+                (&G[0][0])[(ry + 1) * DM_GC + ((rx + 1) >> 1)] = green_at<DM_PW>(&P[ry + 3][rx + DM_PX]);
         }
         __syncthreads();
-        dm_cell<RY, RX, false>(p0, g0, true, true, true, true, red, grn, blu);
+        dm_cell<RY, RX, false, true>(p0, gc0, true, true, true, true, red, grn, blu);
     } else {
         // ---- phase 1, general: one element at a time, coordinates clamped
         for (int ty = wrp; ty < DM_PH; ty += 8) {
@@ -194,7 +204,7 @@ __global__ void __launch_bounds__(256, 8) demosaic_ha_kernel(const DemosaicArgs 
         __syncthreads();
         const int cyy = Y0 + 2 * wrp, cxx = X0 + 2 * lane;
         if (cyy >= H2 || cxx >= W2) return;
-        dm_cell<RY, RX, true>(p0, g0, cyy > 0, cxx > 0, cyy + 2 < H2, cxx + 2 < W2, red, grn, blu);
+        dm_cell<RY, RX, true, false>(p0, g0, cyy > 0, cxx > 0, cyy + 2 < H2, cxx + 2 < W2, red, grn, blu);
     }
 
     // ---- output
